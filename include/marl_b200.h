@@ -1,0 +1,174 @@
+/* marl_b200.h — C-ABI of the B200-native MAPPO rollout-and-update hot path.
+ *
+ * The reference (Desperodoo/distributed_multi_agent_reinforcement_learning) is pure Python and has no FFI
+ * of its own; its plugin surface is Python duck typing resolved by hydra `_target_` strings
+ * (config.yaml:14-15,56-57; runner.py:19,84-85).  This header is the boundary a maintainer binds with
+ * ctypes: every entry point below replaces the body of one reference method and is
+ * cited with the reference file:line it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain C, `extern "C"`, raw pointers + explicit sizes; no torch / C++ types cross the boundary;
+ *   - every pointer named d_* is a DEVICE pointer (HBM) owned by the caller; the library never allocates,
+ *     frees or synchronises; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - returns 0 (MARL_OK) or a negative MARL_E* code; never throws, never exits;
+ *     marl_last_error_string() describes the most recent failure on the calling thread;
+ *   - no global mutable state besides that thread-local error string: re-entrant, one host thread per GPU.
+ *
+ * Layouts (row-major, "pursuer" == reference "defender", "evader" == reference "attacker"):
+ *   p_state   f64 [B,N,4]   (x,y,vx,vy)             base_env.py:198-209, pursuit_env.py:179-180
+ *   e_state   f64 [B,4]
+ *   grid bits u32 [M,W,HW]  HW=ceil(H/32); bit (y&31) of word [m,x,y>>5] == occupied_map.grid_map[x][y]
+ *   raser     u32 [M,W*H,OW] OW=ceil(O/32); bit k of row (x*H+y) == raser_map[x][y][k]  pursuit_env.py:29-53
+ *   map_id    i32 [B]       env b uses map map_id[b] of the pool (NULL => map b)
+ */
+#ifndef MARL_B200_H
+#define MARL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MARL_ABI_VERSION 1
+
+enum {
+    MARL_OK = 0,
+    MARL_EINVAL = -1,     /* bad argument (null pointer, size out of the supported range) */
+    MARL_ECUDA = -2,      /* a CUDA runtime call / kernel launch failed */
+    MARL_EUNSUPPORTED = -3
+};
+
+#define MARL_MAX_AGENTS 128   /* N <= 128 (one warp per env, up to 4 pursuers per lane) */
+#define MARL_NUM_ACTIONS 9    /* agent.py:57-60: 8 headings + stop */
+
+/* Scalar configuration of one Pursuit_Env family (config.yaml:13-54 / conf/{env,attacker,defender,sensor,mao}.yaml). */
+typedef struct marl_env_params {
+    int32_t W, H;              /* map.map_size */
+    int32_t N;                 /* env.num_defender */
+    int32_t O;                 /* map.num_max_obstacle: padded width of every obstacle-adjacency row */
+    int32_t max_steps;         /* env.max_steps */
+    int32_t difficulty;        /* env.difficulty: evader replans every `difficulty` steps */
+    int32_t sensor_beams;      /* sensor.num_beams */
+    int32_t sensor_radius;     /* sensor.radius */
+    int32_t e_extend_dis;      /* attacker.extend_dis */
+    int32_t e_sen_range;       /* attacker.sen_range (window of Evader.rescan) */
+    double d_step, d_tau, d_vmax, d_collision_radius, d_comm_range, d_sen_range;   /* defender.* */
+    double e_step, e_tau, e_vmax, e_collision_radius;                               /* attacker.* */
+    double resolution;         /* map.resolution */
+} marl_env_params;
+
+int marl_version(void);
+const char *marl_last_error_string(void);
+
+/* ---- kernel 1: batched pursuer step --------------------------------------------------------------
+ * Replaces Pursuit_Env.step + defender_reward + collision_detection + Agent.step/dynamic
+ * (environment/pursuit_evasion_game/pursuit_env.py:104-177, agent.py:62-104, Occupied_Grid_Map.py:65-115).
+ * d_action_table f64 [9,2] is Agent.actions_mat (agent.py:57-60) computed by the caller with numpy so that
+ * cos/sin come from the same libm the reference would use.
+ * In/out: d_p_state, d_time_step (i32 [B], += 1), d_collision (u8 [B], sticky OR of any rejected move).
+ * Out: d_reward i32 [B,N], d_can_apply u8 [B,N], d_done u8 [B] (time_step >= max_steps). */
+int marl_env_step(const marl_env_params *p, int32_t B, int32_t M,
+                  double *d_p_state, const double *d_e_state, const int32_t *d_action,
+                  const uint32_t *d_grid_bits, const int32_t *d_map_id, const double *d_action_table,
+                  int32_t *d_reward, uint8_t *d_can_apply, uint8_t *d_collision, int32_t *d_time_step,
+                  uint8_t *d_done, void *stream);
+
+/* ---- kernel 2: observations ----------------------------------------------------------------------
+ * Replaces Pursuit_Env.communicate (pursuit_env.py:182-195, including the `adj_mat[j, 1] = 1` quirk) and
+ * Pursuit_Env.sensor + Pursuer.find_attacker + bresenham_line (pursuit_env.py:197-209, agent.py:157-169,319-341).
+ * Packed outputs (canonical): d_p_adj_bits u32 [B,N,NW] NW=ceil(N/32); d_e_adj u8 [B,N]; d_o_adj_bits u32 [B,N,OW].
+ * Dense outputs (reference ReplayBuffer layout, any may be NULL): d_p_adj_f32 [B,N,N], d_e_adj_f32 [B,N,1],
+ * d_o_adj_f32 [B,N,O]. */
+int marl_env_observe(const marl_env_params *p, int32_t B, int32_t M,
+                     const double *d_p_state, const double *d_e_state,
+                     const uint32_t *d_grid_bits, const uint32_t *d_raser_bits, const int32_t *d_map_id,
+                     uint32_t *d_p_adj_bits, uint8_t *d_e_adj, uint32_t *d_o_adj_bits,
+                     float *d_p_adj_f32, float *d_e_adj_f32, float *d_o_adj_f32, void *stream);
+
+/* ---- kernel 2b: per-map sensor tables ------------------------------------------------------------
+ * Replaces get_boundary_map + get_raser_map (pursuit_env.py:18-53; find_boundaries(mode='inner') is
+ * scikit-image 0.19.3, restated).  d_beam_dir f64 [beams,2] = (cos,sin)(beam*2*pi/beams) from the caller's numpy.
+ * Out: d_boundary_bits u32 [M,W,HW]; d_boundary_count i32 [M]; d_boundary_xy i32 [M,O,2] (np.argwhere order,
+ * rows >= count are zero); d_raser_bits u32 [M,W*H,OW].  A map with more than O boundary cells sets
+ * count to the true number and truncates the list (the reference would raise on buffer store). */
+int marl_raser_map_build(const marl_env_params *p, int32_t M, const uint32_t *d_grid_bits,
+                         const double *d_beam_dir, uint32_t *d_boundary_bits, int32_t *d_boundary_count,
+                         int32_t *d_boundary_xy, uint32_t *d_raser_bits, void *stream);
+
+/* ---- kernel 1c: evader (A* replanning + waypoint following) --------------------------------------
+ * Replaces Pursuit_Env.attacker_step + Evader.{replan,rescan,waypoint2phi,step} + AStar_2D.searching
+ * (pursuit_env.py:75-102, agent.py:197-271, astar.py:26-161, Occupied_Grid_Map.py:119-191).
+ * One call == one attacker_step for B envs.  State per env: d_e_state f64 [B,4] (in/out), d_target i32 [B,2]
+ * (in/out), d_path i16 [B,path_cap,2] + d_path_len i32 [B] (in/out; path[len-1] is the next waypoint, as in the
+ * reference list), d_time_step i32 [B] (read: replan iff time_step % difficulty == 0).
+ * Target resampling (base_env.py:52-70 via pursuit_env.py:98-100) consumes candidates from
+ * d_target_tape i32 [B,tape_len,2] at cursor d_tape_pos i32 [B] (in/out): candidates occupied in the
+ * 2-inflated map are skipped exactly like the rejection loop.  d_inflated_bits u32 [M,W,HW].
+ * d_scratch: >= marl_evader_scratch_bytes(p) * B bytes. */
+int64_t marl_evader_scratch_bytes(const marl_env_params *p);
+int marl_evader_step(const marl_env_params *p, int32_t B, int32_t M,
+                     double *d_e_state, const double *d_p_state, int32_t *d_target,
+                     int16_t *d_path, int32_t *d_path_len, int32_t path_cap,
+                     const int32_t *d_time_step,
+                     const uint32_t *d_grid_bits, const uint32_t *d_inflated_bits, const int32_t *d_map_id,
+                     const int32_t *d_target_tape, int32_t tape_len, int32_t *d_tape_pos,
+                     void *d_scratch, void *stream);
+
+/* ---- kernel 3a: Welford reward normalisation -----------------------------------------------------
+ * Replaces Normalization.__call__ / RunningMeanStd.update (DHGN/normalization.py:4-35) applied per env:
+ * d_n i64 [B], d_mean f64 [B,N], d_S f64 [B,N], d_std f64 [B,N] (in/out); d_reward i32 [B,N] in;
+ * d_out f32 [B,N] = float32((x-mean)/(std+1e-8)) (DHGN/mappo_parallel.py:795-797). update != 0 => update stats. */
+int marl_welford_update(int32_t B, int32_t N, const int32_t *d_reward, int64_t *d_n, double *d_mean,
+                        double *d_S, double *d_std, float *d_out, int32_t update, void *stream);
+
+/* ---- kernel 3b: GAE + advantage normalisation ----------------------------------------------------
+ * Replaces MAPPO.train's GAE block (DHGN/mappo_parallel.py:643-658).  r, active f32 [B,T,N]; v f32 [B,T+1,N].
+ * Out: adv, v_target f32 [B,T,N].  If use_adv_norm, adv = (adv-mean)/(std_unbiased+1e-5)*active over the whole
+ * tensor.  d_workspace: >= marl_gae_workspace_bytes(B,T,N) bytes. */
+int64_t marl_gae_workspace_bytes(int32_t B, int32_t T, int32_t N);
+int marl_gae(int32_t B, int32_t T, int32_t N, const float *d_r, const float *d_v, const float *d_active,
+             float gamma, float lamda_gamma, int32_t use_adv_norm, float *d_adv, float *d_v_target,
+             void *d_workspace, void *stream);
+
+/* ---- kernel 4: minibatch gather ------------------------------------------------------------------
+ * Replaces `batch[key][index]` (DHGN/mappo_parallel.py:665-679): copies rows d_index[i] (i < n_index) of a
+ * [B,row_bytes] byte matrix into [n_index,row_bytes].  row_bytes must be a multiple of 4; 16-byte aligned
+ * rows take the vectorised path. */
+int marl_gather_rows(const void *d_src, void *d_dst, const int64_t *d_index, int32_t n_index,
+                     int64_t row_bytes, int64_t n_src_rows, void *stream);
+
+/* ---- fused rollout (env-only hot loop with a device-side action source) --------------------------
+ * K consecutive iterations of the reference rollout body (DHGN/mappo_parallel.py:758-801) without the
+ * network: observe -> [evader tape] -> step -> reward-norm -> store.  Actions come from d_action_tape
+ * i32 [K,B,N] or, when NULL, from a counter-based uniform{0..8} generator seeded by `seed` (throughput runs).
+ * Evader states come from d_e_tape f64 [K+1,B,4] (state before each iteration's attacker_step at [k], after at
+ * [k+1]).  Records, per iteration k (t0 = first time index): packed observation words and fp32 scalars in the
+ * rollout arena layout of DESIGN.md §3.  Any record pointer may be NULL. */
+typedef struct marl_rollout_records {
+    float *p_state_f32;        /* [B,T,N,4]  float32(p_state before the step)  replay_buffer.py:47 */
+    float *e_state_f32;        /* [B,T,1,4]                                    replay_buffer.py:48 */
+    uint32_t *p_adj_bits;      /* [B,T,N,NW] */
+    uint8_t *e_adj;            /* [B,T,N]    */
+    uint32_t *o_adj_bits;      /* [B,T,N,OW] */
+    float *a_n;                /* [B,T,N]    float32(action)                   replay_buffer.py:57 */
+    float *r;                  /* [B,T,N]    normalised reward                 replay_buffer.py:59 */
+    int32_t *raw_reward;       /* [B,T,N]    un-normalised integer reward */
+    float *active;             /* [B,T,N]    always 1                          mappo_parallel.py:798 */
+    float *p_adj_f32;          /* [B,T,N,N]  dense reference layout (optional) replay_buffer.py:50 */
+    float *e_adj_f32;          /* [B,T,N,1] */
+    float *o_adj_f32;          /* [B,T,N,O] */
+} marl_rollout_records;
+
+int marl_rollout_steps(const marl_env_params *p, int32_t B, int32_t M, int32_t T, int32_t t0, int32_t K,
+                       double *d_p_state, const double *d_e_tape, const int32_t *d_action_tape, uint64_t seed,
+                       const uint32_t *d_grid_bits, const uint32_t *d_raser_bits, const int32_t *d_map_id,
+                       const double *d_action_table,
+                       int64_t *d_wf_n, double *d_wf_mean, double *d_wf_S, double *d_wf_std,
+                       uint8_t *d_collision, int32_t *d_time_step,
+                       const marl_rollout_records *rec, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARL_B200_H */
