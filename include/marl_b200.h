@@ -105,15 +105,19 @@ int marl_raser_map_build(const marl_env_params *p, int32_t M, const uint32_t *d_
  * Target resampling (base_env.py:52-70 via pursuit_env.py:98-100) consumes candidates from
  * d_target_tape i32 [B,tape_len,2] at cursor d_tape_pos i32 [B] (in/out): candidates occupied in the
  * 2-inflated map are skipped exactly like the rejection loop.  d_inflated_bits u32 [M,W,HW].
- * d_scratch: >= marl_evader_scratch_bytes(p) * B bytes. */
-int64_t marl_evader_scratch_bytes(const marl_env_params *p);
+ * d_status i32 [B] (may be NULL) is OR-ed with MARL_EV_* bits; a non-zero status means the result for that env
+ * is NOT the reference's (search heap or path buffer overflow, tape exhausted) and must be treated as an error.
+ * Supported maps: H <= 63, W <= 254 (one 64-bit column per x in shared memory). */
+#define MARL_EV_HEAP_OVERFLOW 1
+#define MARL_EV_PATH_OVERFLOW 2
+#define MARL_EV_TAPE_EXHAUSTED 4
 int marl_evader_step(const marl_env_params *p, int32_t B, int32_t M,
                      double *d_e_state, const double *d_p_state, int32_t *d_target,
                      int16_t *d_path, int32_t *d_path_len, int32_t path_cap,
                      const int32_t *d_time_step,
                      const uint32_t *d_grid_bits, const uint32_t *d_inflated_bits, const int32_t *d_map_id,
                      const int32_t *d_target_tape, int32_t tape_len, int32_t *d_tape_pos,
-                     void *d_scratch, void *stream);
+                     int32_t *d_status, void *stream);
 
 /* ---- kernel 3a: Welford reward normalisation -----------------------------------------------------
  * Replaces Normalization.__call__ / RunningMeanStd.update (DHGN/normalization.py:4-35) applied per env:
@@ -123,13 +127,15 @@ int marl_welford_update(int32_t B, int32_t N, const int32_t *d_reward, int64_t *
                         double *d_S, double *d_std, float *d_out, int32_t update, void *stream);
 
 /* ---- kernel 3b: GAE + advantage normalisation ----------------------------------------------------
- * Replaces MAPPO.train's GAE block (DHGN/mappo_parallel.py:643-658).  r, active f32 [B,T,N]; v f32 [B,T+1,N].
- * Out: adv, v_target f32 [B,T,N].  If use_adv_norm, adv = (adv-mean)/(std_unbiased+1e-5)*active over the whole
- * tensor.  d_workspace: >= marl_gae_workspace_bytes(B,T,N) bytes. */
+ * Replaces MAPPO.train's GAE block (DHGN/mappo_parallel.py:643-658).  time_major == 0: r, active f32 [B,T,N],
+ * v f32 [B,T+1,N] (reference ReplayBuffer layout); time_major != 0: [T,B,N] / [T+1,B,N] (rollout arena layout).
+ * Out: adv, v_target in the same layout as r.  gamma_lamda = float32(gamma*lamda) with the product taken in
+ * double, as Python does.  If use_adv_norm, adv = (adv-mean)/(std_unbiased+1e-5)*active over the whole tensor.
+ * d_workspace: >= marl_gae_workspace_bytes(B,T,N) bytes. */
 int64_t marl_gae_workspace_bytes(int32_t B, int32_t T, int32_t N);
 int marl_gae(int32_t B, int32_t T, int32_t N, const float *d_r, const float *d_v, const float *d_active,
-             float gamma, float lamda_gamma, int32_t use_adv_norm, float *d_adv, float *d_v_target,
-             void *d_workspace, void *stream);
+             int32_t time_major, float gamma, float gamma_lamda, int32_t use_adv_norm, float *d_adv,
+             float *d_v_target, void *d_workspace, void *stream);
 
 /* ---- kernel 4: minibatch gather ------------------------------------------------------------------
  * Replaces `batch[key][index]` (DHGN/mappo_parallel.py:665-679): copies rows d_index[i] (i < n_index) of a
@@ -143,21 +149,23 @@ int marl_gather_rows(const void *d_src, void *d_dst, const int64_t *d_index, int
  * network: observe -> [evader tape] -> step -> reward-norm -> store.  Actions come from d_action_tape
  * i32 [K,B,N] or, when NULL, from a counter-based uniform{0..8} generator seeded by `seed` (throughput runs).
  * Evader states come from d_e_tape f64 [K+1,B,4] (state before each iteration's attacker_step at [k], after at
- * [k+1]).  Records, per iteration k (t0 = first time index): packed observation words and fp32 scalars in the
- * rollout arena layout of DESIGN.md §3.  Any record pointer may be NULL. */
-typedef struct marl_rollout_records {
-    float *p_state_f32;        /* [B,T,N,4]  float32(p_state before the step)  replay_buffer.py:47 */
-    float *e_state_f32;        /* [B,T,1,4]                                    replay_buffer.py:48 */
-    uint32_t *p_adj_bits;      /* [B,T,N,NW] */
-    uint8_t *e_adj;            /* [B,T,N]    */
-    uint32_t *o_adj_bits;      /* [B,T,N,OW] */
-    float *a_n;                /* [B,T,N]    float32(action)                   replay_buffer.py:57 */
-    float *r;                  /* [B,T,N]    normalised reward                 replay_buffer.py:59 */
-    int32_t *raw_reward;       /* [B,T,N]    un-normalised integer reward */
-    float *active;             /* [B,T,N]    always 1                          mappo_parallel.py:798 */
-    float *p_adj_f32;          /* [B,T,N,N]  dense reference layout (optional) replay_buffer.py:50 */
-    float *e_adj_f32;          /* [B,T,N,1] */
-    float *o_adj_f32;          /* [B,T,N,O] */
+ * [k+1]).  Records for iteration k land at time index t0+k of the TIME-MAJOR rollout arena (the
+ * reference's [B,T,...] tensors are zero-copy permuted views of it).  Any record pointer may be NULL.
+ * Generated actions: uniform{0..8} = ((splitmix64(seed ^ splitmix64(agent*0x100000001B3 + t)) >> 32) * 9) >> 32
+ * with agent = b*N+i and t = t0+k. */
+typedef struct marl_rollout_records {   /* all TIME-MAJOR: one step of all envs is one contiguous slab */
+    float *p_state_f32;        /* [T,B,N,4]  float32(p_state before the step)  replay_buffer.py:47 */
+    float *e_state_f32;        /* [T,B,1,4]                                    replay_buffer.py:48 */
+    uint32_t *p_adj_bits;      /* [T,B,N,NW] */
+    uint8_t *e_adj;            /* [T,B,N]    */
+    uint32_t *o_adj_bits;      /* [T,B,N,OW] */
+    float *a_n;                /* [T,B,N]    float32(action)                   replay_buffer.py:57 */
+    float *r;                  /* [T,B,N]    normalised reward                 replay_buffer.py:59 */
+    int32_t *raw_reward;       /* [T,B,N]    un-normalised integer reward */
+    float *active;             /* [T,B,N]    always 1                          mappo_parallel.py:798 */
+    float *p_adj_f32;          /* [T,B,N,N]  dense fp32 as the reference stores it (optional) replay_buffer.py:50 */
+    float *e_adj_f32;          /* [T,B,N,1] */
+    float *o_adj_f32;          /* [T,B,N,O] */
 } marl_rollout_records;
 
 int marl_rollout_steps(const marl_env_params *p, int32_t B, int32_t M, int32_t T, int32_t t0, int32_t K,
