@@ -67,7 +67,7 @@ _PROTOTYPES = {
     "marl_env_observe": (C.c_int, [_PP, _I32, _I32] + [_VP] * 12),
     "marl_raser_map_build": (C.c_int, [_PP, _I32] + [_VP] * 7),
     "marl_evader_step": (C.c_int, [_PP, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _I32, _VP,
-                                   _VP, _VP]),
+                                   _VP, _VP, _VP]),
     "marl_welford_update": (C.c_int, [_I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _VP]),
     "marl_gae_workspace_bytes": (_I64, [_I32, _I32, _I32]),
     "marl_gae": (C.c_int, [_I32, _I32, _I32, _VP, _VP, _VP, _I32, _F32, _F32, _I32, _VP, _VP, _VP, _VP]),

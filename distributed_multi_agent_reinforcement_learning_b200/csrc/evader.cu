@@ -28,6 +28,7 @@ struct EvaderArgs {
     const int32_t *target_tape;
     int32_t *tape_pos;
     int32_t *status;
+    double *e_tape2;   // optional [2,B,4]: evader state before / after this attacker_step
 };
 
 __device__ __forceinline__ uint64_t col_of(const uint32_t *bits, int HW, int x)
@@ -280,6 +281,11 @@ evader_kernel(EnvDev c, EvaderArgs r)
             r.target[2 * b] = tx;
             r.target[2 * b + 1] = ty;
         }
+        if (r.e_tape2) {   // the 2-slot tape the rollout kernel consumes: [0]=before, [1]=after attacker_step
+            double *t0 = r.e_tape2 + 4 * (size_t)b, *t1 = r.e_tape2 + 4 * ((size_t)r.B + b);
+            t0[0] = ex; t0[1] = ey; t0[2] = evx; t0[3] = evy;
+            t1[0] = r.e_state[4 * b]; t1[1] = r.e_state[4 * b + 1]; t1[2] = r.e_state[4 * b + 2]; t1[3] = r.e_state[4 * b + 3];
+        }
         r.path_len[b] = plen;
         if (r.status) r.status[b] |= status;
     }
@@ -299,7 +305,7 @@ extern "C" int marl_evader_step(const marl_env_params *p, int32_t B, int32_t M, 
                                 const double *d_p_state, int32_t *d_target, int16_t *d_path, int32_t *d_path_len,
                                 int32_t path_cap, const int32_t *d_time_step, const uint32_t *d_grid_bits,
                                 const uint32_t *d_inflated_bits, const int32_t *d_map_id, const int32_t *d_target_tape,
-                                int32_t tape_len, int32_t *d_tape_pos, int32_t *d_status, void *stream)
+                                int32_t tape_len, int32_t *d_tape_pos, int32_t *d_status, double *d_e_tape2, void *stream)
 {
     EnvDev c;
     int rc = make_env_dev(p, &c);
@@ -320,7 +326,7 @@ extern "C" int marl_evader_step(const marl_env_params *p, int32_t B, int32_t M, 
     r.B = B; r.path_cap = path_cap; r.tape_len = tape_len;
     r.e_state = d_e_state; r.p_state = d_p_state; r.target = d_target; r.path = d_path; r.path_len = d_path_len;
     r.time_step = d_time_step; r.grid_bits = d_grid_bits; r.inflated_bits = d_inflated_bits; r.map_id = d_map_id;
-    r.target_tape = d_target_tape; r.tape_pos = d_tape_pos; r.status = d_status;
+    r.target_tape = d_target_tape; r.tape_pos = d_tape_pos; r.status = d_status; r.e_tape2 = d_e_tape2;
     evader_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(c, r);
     return check_launch("evader_kernel");
 }

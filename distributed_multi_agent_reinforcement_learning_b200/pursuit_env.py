@@ -181,14 +181,15 @@ class BatchedPursuitEnv:
         self.launches += 1
         return d if dense else (self.p_adj_bits, self.e_adj, self.o_adj_bits)
 
-    def evader_step(self):
-        """attacker_step() for all envs (A* replanning every `difficulty` steps + waypoint following)."""
+    def evader_step(self, e_tape2=None):
+        """attacker_step() for all envs (A* replanning every `difficulty` steps + waypoint following).
+        e_tape2: optional f64 [2,B,4] receiving the evader state before/after (feeds rollout(K=1))."""
         _lib.check(self.lib.marl_evader_step(
             self._pp(), self.B, self.M, _lib.ptr(self.e_state), _lib.ptr(self.p_state), _lib.ptr(self.target),
             _lib.ptr(self.path), _lib.ptr(self.path_len), self.PATH_CAP, _lib.ptr(self.time_step),
             _lib.ptr(self.grid_bits), _lib.ptr(self.inflated_bits), _lib.ptr(self.map_id),
             _lib.ptr(self.target_tape), self._tape_len, _lib.ptr(self.tape_pos), _lib.ptr(self.evader_status),
-            _lib.stream_ptr()), "marl_evader_step")
+            _lib.ptr(e_tape2), _lib.stream_ptr()), "marl_evader_step")
         self.launches += 1
 
     def step(self, action):
@@ -213,7 +214,7 @@ class BatchedPursuitEnv:
         self.launches += 1
         return self.r_norm
 
-    def rollout(self, arena, K, t0=0, e_tape=None, action_tape=None, seed=0):
+    def rollout(self, arena, K, t0=0, e_tape=None, action_tape=None, seed=0, sync_evader=True):
         """K fused env-only iterations (observe -> evader tape -> step -> reward-norm -> store) in ONE launch.
         arena: RolloutArena.  e_tape f64 [K+1,B,4]; action_tape i32 [K,B,N] or None (counter-based uniform)."""
         assert e_tape is not None and tuple(e_tape.shape) == (K + 1, self.B, 4) and e_tape.dtype == torch.float64
@@ -228,7 +229,54 @@ class BatchedPursuitEnv:
             _lib.ptr(self.wf_S), _lib.ptr(self.wf_std), _lib.ptr(self.collision), _lib.ptr(self.time_step),
             ctypes.byref(rec), _lib.stream_ptr()), "marl_rollout_steps")
         self.launches += 1
-        self.e_state.copy_(e_tape[K])
+        if sync_evader:
+            self.e_state.copy_(e_tape[K])
+
+    def rollout_closed(self, arena, K, t0=0, action_tape=None, seed=0):
+        """K closed-loop env iterations with the A* evader on the GPU: per iteration one evader launch (writes the
+        before/after evader states) and one fused observe/step/reward-norm/store launch.  Nothing touches the host,
+        so the whole sequence can be captured in a CUDA graph (see EpisodeGraph)."""
+        if getattr(self, "_e_tape2", None) is None:
+            self._e_tape2 = torch.zeros(2, self.B, 4, dtype=torch.float64, device=self.device)
+        for k in range(K):
+            self.evader_step(self._e_tape2)
+            self.rollout(arena, 1, t0 + k, e_tape=self._e_tape2,
+                         action_tape=None if action_tape is None else action_tape[k:k + 1], seed=seed, sync_evader=False)
+
+    def snapshot(self):
+        """Device-side copy of everything an episode mutates (for replaying identical episodes)."""
+        names = ("p_state", "e_state", "target", "path", "path_len", "time_step", "collision", "done", "tape_pos",
+                 "evader_status", "wf_n", "wf_mean", "wf_S", "wf_std")
+        return {n: getattr(self, n).clone() for n in names}
+
+    def restore(self, snap):
+        for n, t in snap.items():
+            getattr(self, n).copy_(t)
+
+
+class EpisodeGraph:
+    """One whole closed-loop episode (T env steps = 2T kernel launches) captured in a CUDA graph: the rollout inner
+    loop is launch-bound at 4096 envs, so the graph removes ~2T host launch latencies per episode."""
+
+    def __init__(self, env, arena, T, seed=0):
+        self.env, self.arena, self.T = env, arena, T
+        snap = env.snapshot()
+        env.rollout_closed(arena, T, 0, seed=seed)          # eager warm-up (also sets kernel attributes)
+        torch.cuda.synchronize()
+        env.restore(snap)
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(self.graph, stream=side):
+                env.rollout_closed(arena, T, 0, seed=seed)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        env.restore(snap)
+        self.launches_per_replay = 2 * T
+
+    def replay(self):
+        self.graph.replay()
 
 
 class RolloutArena:

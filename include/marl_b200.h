@@ -107,6 +107,8 @@ int marl_raser_map_build(const marl_env_params *p, int32_t M, const uint32_t *d_
  * 2-inflated map are skipped exactly like the rejection loop.  d_inflated_bits u32 [M,W,HW].
  * d_status i32 [B] (may be NULL) is OR-ed with MARL_EV_* bits; a non-zero status means the result for that env
  * is NOT the reference's (search heap or path buffer overflow, tape exhausted) and must be treated as an error.
+ * d_e_tape2 f64 [2,B,4] (may be NULL) receives the evader state before ([0]) and after ([1]) this step — the
+ * 2-slot tape marl_rollout_steps(K=1) consumes, so a closed-loop env step is two launches.
  * Supported maps: H <= 63, W <= 254 (one 64-bit column per x in shared memory). */
 #define MARL_EV_HEAP_OVERFLOW 1
 #define MARL_EV_PATH_OVERFLOW 2
@@ -117,7 +119,7 @@ int marl_evader_step(const marl_env_params *p, int32_t B, int32_t M,
                      const int32_t *d_time_step,
                      const uint32_t *d_grid_bits, const uint32_t *d_inflated_bits, const int32_t *d_map_id,
                      const int32_t *d_target_tape, int32_t tape_len, int32_t *d_tape_pos,
-                     int32_t *d_status, void *stream);
+                     int32_t *d_status, double *d_e_tape2, void *stream);
 
 /* ---- kernel 3a: Welford reward normalisation -----------------------------------------------------
  * Replaces Normalization.__call__ / RunningMeanStd.update (DHGN/normalization.py:4-35) applied per env:

@@ -505,6 +505,50 @@ void orc_rollout_iteration(const marl_env_params *p, int32_t B, double *p_state,
     }
 }
 
+
+/* Closed env-only rollout iteration WITH the A* evader (the reference loop body DHGN/mappo_parallel.py:758-801 minus
+ * the network): observe -> attacker_step -> step -> reward-norm, for B envs on all host threads.
+ * Evader state per env: e_state [B,4], target [B,2], path i16 [B,cap,2], path_len [B]; target tape [B,tape_len,2]. */
+void orc_rollout_iteration_closed(const marl_env_params *p, int32_t B, double *p_state, double *e_state,
+                                  int32_t *target, int16_t *path, int32_t *path_len, int32_t cap,
+                                  const int32_t *action, const uint8_t *grid, const uint8_t *inflated,
+                                  const uint8_t *raser, const int32_t *ob_count, int32_t ob_stride,
+                                  const int32_t *map_id, const double *action_table, const int32_t *tape,
+                                  int32_t tape_len, int32_t *tape_pos, uint8_t *p_adj, uint8_t *o_adj, uint8_t *e_adj,
+                                  int32_t *reward, uint8_t *can_apply, uint8_t *collision, int32_t *time_step,
+                                  uint8_t *done, int64_t *wf_n, double *wf_mean, double *wf_S, double *wf_std,
+                                  float *r_norm, int32_t *status)
+{
+    int N = p->N, O = p->O, WH = p->W * p->H;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int b = 0; b < B; b++) {
+        int m = map_id ? map_id[b] : b;
+        const uint8_t *g = grid + (size_t)m * WH;
+        const uint8_t *rs = raser + (size_t)m * WH * ob_stride;
+        double *ps = p_state + (size_t)b * N * 4;
+        double *es = e_state + (size_t)b * 4;
+        orc_communicate(p, ps, p_adj + (size_t)b * N * N);
+        uint8_t *oa = o_adj + (size_t)b * N * O;
+        memset(oa, 0, (size_t)N * O);
+        for (int i = 0; i < N; i++) {
+            int cx = (int)ps[4 * i], cy = (int)ps[4 * i + 1];
+            const uint8_t *row = rs + ((size_t)cx * p->H + cy) * ob_stride;
+            int ob = ob_count[m] < O ? ob_count[m] : O;
+            memcpy(oa + (size_t)i * O, row, (size_t)ob);
+            e_adj[(size_t)b * N + i] = (uint8_t)orc_find_attacker(p, g, orc_round(ps[4 * i]), orc_round(ps[4 * i + 1]),
+                                                                 orc_round(es[0]), orc_round(es[1]));
+        }
+        int32_t rc = orc_evader_step(p, es, ps, target + 2 * (size_t)b, path + (size_t)b * cap * 2, path_len + b, cap,
+                                     time_step[b], g, inflated + (size_t)m * WH, tape + (size_t)b * tape_len * 2, tape_len,
+                                     tape_pos + b);
+        if (rc && status) status[b] = rc;
+        orc_env_step(p, ps, es, action + (size_t)b * N, g, action_table, reward + (size_t)b * N,
+                     can_apply + (size_t)b * N, collision + b, time_step + b, done + b);
+        orc_welford(N, reward + (size_t)b * N, wf_n + b, wf_mean + (size_t)b * N, wf_S + (size_t)b * N,
+                    wf_std + (size_t)b * N, r_norm + (size_t)b * N, 1);
+    }
+}
+
 int32_t orc_num_threads(void)
 {
 #ifdef _OPENMP

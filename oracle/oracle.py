@@ -221,5 +221,18 @@ def rollout_iteration(p, st):
         _p(st["done"]), _p(st["wf_n"]), _p(st["wf_mean"]), _p(st["wf_S"]), _p(st["wf_std"]), _p(st["r_norm"]))
 
 
+def rollout_iteration_closed(p, st):
+    """As rollout_iteration but with the A* evader in the loop (st carries e_state/target/path/... arrays)."""
+    B = st["p_state"].shape[0]
+    lib().orc_rollout_iteration_closed(
+        C.byref(p), C.c_int32(B), _p(st["p_state"]), _p(st["e_state"]), _p(st["target"]), _p(st["path"]),
+        _p(st["path_len"]), C.c_int32(st["path"].shape[1]), _p(st["action"]), _p(st["grid"]), _p(st["inflated"]),
+        _p(st["raser"]), _p(st["ob_count"]), C.c_int32(st["raser"].shape[-1]), _p(st["map_id"]),
+        _p(st["action_table"]), _p(st["tape"]), C.c_int32(st["tape"].shape[1]), _p(st["tape_pos"]), _p(st["p_adj"]),
+        _p(st["o_adj"]), _p(st["e_adj"]), _p(st["reward"]), _p(st["can_apply"]), _p(st["collision"]),
+        _p(st["time_step"]), _p(st["done"]), _p(st["wf_n"]), _p(st["wf_mean"]), _p(st["wf_S"]), _p(st["wf_std"]),
+        _p(st["r_norm"]), _p(st["status"]))
+
+
 def num_threads():
     return lib().orc_num_threads()
