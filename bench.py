@@ -8,7 +8,8 @@ reward-norm -> store into the time-major rollout arena.  Actions come from the d
 (scripted policy stand-in; the actor/critic network is not in this loop yet — stated in `config.policy`).
 
 metric = agent-env-steps/s = B*N*T / time, whole job (all ranks).
-  value : episode replayed from HBM-resident initial state (CUDA graph of the 2T kernel launches).
+  value : episode replayed from HBM-resident initial state (CUDA graph of 2*T/10 kernel launches: one A* replanning
+          launch + one fused 10-step rollout launch per replanning period).
   e2e   : same episode through the public API with HOST buffers: pinned initial states/targets H2D + episode
           reward sums D2H inside the timed region.
 --impl reference : the CPU oracle port of the same loop (oracle/marl_oracle.c, all host threads) on a bounded
@@ -285,49 +286,28 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * N * T * args.steps / (float(t.item()) * 1e-3)
 
-    # ---- per-kernel durations (CUDA events on the launching stream) and the roofline of the env kernel ---------
-    def kernel_ms(fn, reps):
-        torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for i in range(reps):
-            fn(i)
-        e.record()
-        e.synchronize()
-        return s.elapsed_time(e) / reps
-
+    # ---- per-kernel durations: CUDA events around every launch of one eager episode (same stream) ----------
     env.restore(snap)
-    tape2 = torch.zeros(2, B, 4, dtype=torch.float64, device=dev)
-    tape2[0] = env.e_state
-    tape2[1] = env.e_state
-    # env kernel: the K=1 launches of an episode, replayed from a graph so host launch overhead is excluded
-    g_env = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for k in range(3):
-            env.rollout(arena, 1, k, e_tape=tape2, seed=1, sync_evader=False)
-        with torch.cuda.graph(g_env, stream=side):
-            for k in range(T):
-                env.rollout(arena, 1, k, e_tape=tape2, seed=1, sync_evader=False)
-    torch.cuda.current_stream().wait_stream(side)
-    env.restore(snap)
-    ms_env_episode = kernel_ms(lambda i: (env.time_step.zero_(), g_env.replay()), 5)
-    ms_env = ms_env_episode / T
+    timers = {}
+    env.rollout_closed(arena, T, 0, seed=0xB200 + rank, timers=timers)
+    torch.cuda.synchronize()
+    kernel_table = {k: {"launches": len(v), "total_ms": sum(a.elapsed_time(b) for a, b in v)} for k, v in timers.items()}
+    for v in kernel_table.values():
+        v["avg_us"] = 1e3 * v["total_ms"] / v["launches"]
     env.restore(snap)
     ms_episode = ms_total / args.steps
+    kernel_table["episode_graph_ms"] = ms_episode
     peak, peak_src = measured_peaks()
-    alg_bytes = SURVEY_BYTES_PER_AGENT_STEP * B * N
-    achieved = alg_bytes / (ms_env * 1e-3) / 1e9
-    roofline = {"kernel": "rollout_kernel<8,1> (observe+step+reward-norm+store, K=1 launch)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "avg_launch_us": ms_env * 1e3,
-                "share_of_step": ms_env_episode / ms_episode,
-                "note": "3.9 MB per launch at 4096 envs: latency-bound far below the HBM roof; the A* evader kernel "
-                        "takes the rest of the step (see kernel_ms_per_episode)"}
-    kernel_table = {"rollout_kernel": ms_env_episode, "evader_kernel": max(ms_episode - ms_env_episode, 0.0),
-                    "episode": ms_episode}
+    rk = kernel_table["rollout_kernel(closed)"]
+    steps_per_launch = T / rk["launches"]
+    alg_bytes = SURVEY_BYTES_PER_AGENT_STEP * B * N * steps_per_launch
+    achieved = alg_bytes / (rk["avg_us"] * 1e-6) / 1e9
+    roofline = {"kernel": "rollout_kernel<8,1,closed> (observe + evader move + step + reward-norm + store, %d env steps per launch)" % steps_per_launch,
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                "avg_launch_us": rk["avg_us"], "share_of_step": rk["total_ms"] / sum(v["total_ms"] for k, v in kernel_table.items() if isinstance(v, dict)),
+                "note": "118 B/agent-step (SURVEY 8d) x 32768 agents x 10 steps per launch; working set of one launch fits L2, "
+                        "so this kernel is latency-bound (fp64 RK4 division chains), not HBM-bound, at 4096 envs"}
 
     if rank == 0:
         # ---- CPU baseline: oracle port on the box's host cores, bounded sample ------------------------------

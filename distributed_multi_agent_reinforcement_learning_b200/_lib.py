@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmarl_b200.so")
 
 MARL_OK = 0
-EV_HEAP_OVERFLOW, EV_PATH_OVERFLOW, EV_TAPE_EXHAUSTED = 1, 2, 4
+EV_HEAP_OVERFLOW, EV_PATH_OVERFLOW, EV_TAPE_EXHAUSTED, EV_MISSED_REPLAN = 1, 2, 4, 8
 
 
 class MarlError(RuntimeError):
@@ -68,6 +68,10 @@ _PROTOTYPES = {
     "marl_raser_map_build": (C.c_int, [_PP, _I32] + [_VP] * 7),
     "marl_evader_step": (C.c_int, [_PP, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _I32, _VP,
                                    _VP, _VP, _VP]),
+    "marl_evader_replan": (C.c_int, [_PP, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
+    "marl_rollout_closed": (C.c_int, [_PP, _I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _I32,
+                                      _VP, _VP, _VP, _U64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
+                                      C.POINTER(RolloutRecords), _VP]),
     "marl_welford_update": (C.c_int, [_I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _VP]),
     "marl_gae_workspace_bytes": (_I64, [_I32, _I32, _I32]),
     "marl_gae": (C.c_int, [_I32, _I32, _I32, _VP, _VP, _VP, _I32, _F32, _F32, _I32, _VP, _VP, _VP, _VP]),

@@ -2,6 +2,7 @@
 // sm_100a.  HBM-bound integer/fp64 work: coalesced vectorised state traffic, shared-memory staging of the
 // per-step exchange tiles and of the occupancy bitmap, grids sized to fill 148 SMs.  No tensor cores here.
 #include "env_group.cuh"
+#include "evader_move.cuh"
 #include <type_traits>
 
 namespace marl {
@@ -226,9 +227,20 @@ struct RolloutArgs {
     uint8_t *collision;
     int32_t *time_step;
     marl_rollout_records rec;    // time-major [T,B,N,...]
+    // closed loop (CLOSED=true): the evader's per-step move is done here by the group leader; replanning is a
+    // separate launch at every `difficulty` boundary, so K never crosses one.
+    double *e_state;             // [B,4] in/out
+    int32_t *target;             // [B,2] in/out
+    const int16_t *path;         // [B,path_cap,2]
+    int32_t *path_len;           // [B] in/out
+    int path_cap, tape_len;
+    const uint32_t *inflated_bits;
+    const int32_t *target_tape;  // [B,tape_len,2]
+    int32_t *tape_pos;           // [B] in/out
+    int32_t *ev_status;          // [B] OR-ed
 };
 
-template <int G, int APL>
+template <int G, int APL, bool CLOSED>
 __global__ void __launch_bounds__(kThreads)
 rollout_kernel(EnvDev c, RolloutArgs r)
 {
@@ -285,9 +297,21 @@ rollout_kernel(EnvDev c, RolloutArgs r)
     uint32_t *s_words = s_words_all + (size_t)warp * (32 * APL) * (c.OW + c.NW);
     const int64_t BN = (int64_t)B * N;
     double2 e_cur = make_double2(0.0, 0.0), e_vel = make_double2(0.0, 0.0);
+    const double *e_src = CLOSED ? r.e_state : r.e_tape;
     if (env_ok) {
-        e_cur = *reinterpret_cast<const double2 *>(r.e_tape + 4 * g.env);
-        e_vel = *reinterpret_cast<const double2 *>(r.e_tape + 4 * g.env + 2);
+        e_cur = *reinterpret_cast<const double2 *>(e_src + 4 * g.env);
+        e_vel = *reinterpret_cast<const double2 *>(e_src + 4 * g.env + 2);
+    }
+    EvaderRegs ev;
+    ev.x = ev.y = ev.vx = ev.vy = 0.0;
+    ev.tx = ev.ty = ev.plen = ev.tape_pos = ev.status = 0;
+    const int leader = g.sub * G;
+    const bool is_leader = env_ok && g.gl == 0;
+    if (CLOSED && is_leader) {
+        ev.tx = r.target[2 * g.env];
+        ev.ty = r.target[2 * g.env + 1];
+        ev.plen = r.path_len[g.env];
+        ev.tape_pos = r.tape_pos[g.env];
     }
     for (int k = 0; k < r.K; ++k) {
         const int t = r.t0 + k;
@@ -295,7 +319,20 @@ rollout_kernel(EnvDev c, RolloutArgs r)
         // prefetch the evader state after this iteration's attacker_step and the actions (independent of observe)
         double2 e_nxt = e_cur, e_nvel = e_vel;
         int act[APL];
-        if (env_ok) {
+        if (CLOSED) {
+            // attacker_step's move (pursuit_env.py:84-100) by the group leader, then broadcast to the group
+            if (is_leader) {
+                if (k > 0 && (ts % c.difficulty) == 0) ev.status |= EV_MISSED_REPLAN;
+                ev.x = e_cur.x; ev.y = e_cur.y; ev.vx = e_vel.x; ev.vy = e_vel.y;
+                evader_move(c, s_grid, r.inflated_bits + (size_t)(r.map_id ? r.map_id[g.env] : (int)g.env) * grid_words,
+                            r.path + (size_t)g.env * r.path_cap * 2, r.target_tape + (size_t)g.env * r.tape_len * 2,
+                            r.tape_len, ev);
+            }
+            e_nxt.x = __shfl_sync(0xffffffffu, ev.x, leader);
+            e_nxt.y = __shfl_sync(0xffffffffu, ev.y, leader);
+            e_nvel.x = __shfl_sync(0xffffffffu, ev.vx, leader);
+            e_nvel.y = __shfl_sync(0xffffffffu, ev.vy, leader);
+        } else if (env_ok) {
             const double *ep = r.e_tape + ((int64_t)(k + 1) * B + g.env) * 4;
             e_nxt = *reinterpret_cast<const double2 *>(ep);
             e_nvel = *reinterpret_cast<const double2 *>(ep + 2);
@@ -374,6 +411,15 @@ rollout_kernel(EnvDev c, RolloutArgs r)
         if (r.wf_n) r.wf_n[g.env] = wn;
         r.time_step[g.env] = ts;
         if (coll && r.collision) r.collision[g.env] = 1;
+        if (CLOSED) {
+            *reinterpret_cast<double2 *>(r.e_state + 4 * g.env) = e_cur;
+            *reinterpret_cast<double2 *>(r.e_state + 4 * g.env + 2) = e_vel;
+            r.target[2 * g.env] = ev.tx;
+            r.target[2 * g.env + 1] = ev.ty;
+            r.path_len[g.env] = ev.plen;
+            r.tape_pos[g.env] = ev.tape_pos;
+            if (r.ev_status && ev.status) r.ev_status[g.env] |= ev.status;
+        }
     }
 }
 
@@ -449,6 +495,27 @@ extern "C" int marl_env_observe(const marl_env_params *p, int32_t B, int32_t M, 
     });
 }
 
+static int launch_rollout(const EnvDev &c, RolloutArgs &r, bool closed, cudaStream_t s)
+{
+    return dispatch_group(c.N, [&](auto Gc, auto Ac) -> int {
+        constexpr int G = decltype(Gc)::value, APL = decltype(Ac)::value;
+        constexpr int EPW = 32 / G;
+        const size_t smem = (size_t)kWarpsPerBlock * 2 * 32 * APL * sizeof(double2) + (2 * MARL_NUM_ACTIONS + 2) * sizeof(double) +
+                            (size_t)kWarpsPerBlock * EPW * c.W * c.HW * sizeof(uint32_t) +
+                            (size_t)kWarpsPerBlock * 32 * APL * (c.OW + c.NW) * sizeof(uint32_t);
+        MARL_REQUIRE(smem <= 227 * 1024, "marl_rollout: %zu B shared memory needed", smem);
+        auto go = [&](auto kernel) -> int {
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) { set_error("rollout: smem %zu: %s", smem, cudaGetErrorString(e)); return (int)MARL_ECUDA; }
+            }
+            kernel<<<blocks_for(r.B, EPW), kThreads, smem, s>>>(c, r);
+            return check_launch("rollout_kernel");
+        };
+        return closed ? go(rollout_kernel<G, APL, true>) : go(rollout_kernel<G, APL, false>);
+    });
+}
+
 extern "C" int marl_rollout_steps(const marl_env_params *p, int32_t B, int32_t M, int32_t T, int32_t t0, int32_t K,
                                   double *d_p_state, const double *d_e_tape, const int32_t *d_action_tape, uint64_t seed,
                                   const uint32_t *d_grid_bits, const uint32_t *d_raser_bits, const int32_t *d_map_id,
@@ -464,25 +531,44 @@ extern "C" int marl_rollout_steps(const marl_env_params *p, int32_t B, int32_t M
                  "marl_rollout_steps: null pointer");
     MARL_REQUIRE(d_map_id || M >= B, "marl_rollout_steps: map_id is NULL but M < B");
     MARL_REQUIRE(!d_wf_n || (d_wf_mean && d_wf_S && d_wf_std), "marl_rollout_steps: partial Welford state");
-    RolloutArgs r;
+    RolloutArgs r = {};
     r.B = B; r.T = T; r.t0 = t0; r.K = K;
     r.p_state = d_p_state; r.e_tape = d_e_tape; r.action_tape = d_action_tape; r.seed = seed;
     r.grid_bits = d_grid_bits; r.raser_bits = d_raser_bits; r.map_id = d_map_id; r.action_table = d_action_table;
     r.wf_n = (long long *)d_wf_n; r.wf_mean = d_wf_mean; r.wf_S = d_wf_S; r.wf_std = d_wf_std;
     r.collision = d_collision; r.time_step = d_time_step; r.rec = *rec;
-    cudaStream_t s = (cudaStream_t)stream;
-    return dispatch_group(c.N, [&](auto Gc, auto Ac) -> int {
-        constexpr int G = decltype(Gc)::value, APL = decltype(Ac)::value;
-        constexpr int EPW = 32 / G;
-        const size_t smem = (size_t)kWarpsPerBlock * 2 * 32 * APL * sizeof(double2) + (2 * MARL_NUM_ACTIONS + 2) * sizeof(double) +
-                            (size_t)kWarpsPerBlock * EPW * c.W * c.HW * sizeof(uint32_t) +
-                            (size_t)kWarpsPerBlock * 32 * APL * (c.OW + c.NW) * sizeof(uint32_t);
-        MARL_REQUIRE(smem <= 227 * 1024, "marl_rollout_steps: %zu B shared memory needed", smem);
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(rollout_kernel<G, APL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { set_error("rollout: smem %zu: %s", smem, cudaGetErrorString(e)); return (int)MARL_ECUDA; }
-        }
-        rollout_kernel<G, APL><<<blocks_for(B, EPW), kThreads, smem, s>>>(c, r);
-        return check_launch("rollout_kernel");
-    });
+    return launch_rollout(c, r, false, (cudaStream_t)stream);
+}
+
+extern "C" int marl_rollout_closed(const marl_env_params *p, int32_t B, int32_t M, int32_t T, int32_t t0, int32_t K,
+                                   double *d_p_state, double *d_e_state, int32_t *d_target, const int16_t *d_path,
+                                   int32_t *d_path_len, int32_t path_cap, const uint32_t *d_inflated_bits,
+                                   const int32_t *d_target_tape, int32_t tape_len, int32_t *d_tape_pos,
+                                   int32_t *d_evader_status, const int32_t *d_action_tape, uint64_t seed,
+                                   const uint32_t *d_grid_bits, const uint32_t *d_raser_bits, const int32_t *d_map_id,
+                                   const double *d_action_table, int64_t *d_wf_n, double *d_wf_mean, double *d_wf_S,
+                                   double *d_wf_std, uint8_t *d_collision, int32_t *d_time_step,
+                                   const marl_rollout_records *rec, void *stream)
+{
+    EnvDev c;
+    int rc = make_env_dev(p, &c);
+    if (rc) return rc;
+    MARL_REQUIRE(B > 0 && M > 0 && K > 0 && t0 >= 0 && t0 + K <= T, "marl_rollout_closed: B=%d M=%d T=%d t0=%d K=%d", B, M, T, t0, K);
+    MARL_REQUIRE(K <= c.difficulty, "marl_rollout_closed: K=%d crosses a replanning boundary (difficulty=%d)", K, c.difficulty);
+    MARL_REQUIRE(d_p_state && d_e_state && d_target && d_path && d_path_len && d_inflated_bits && d_tape_pos &&
+                     (d_target_tape || tape_len == 0) && d_grid_bits && d_raser_bits && d_action_table && d_time_step && rec,
+                 "marl_rollout_closed: null pointer");
+    MARL_REQUIRE(path_cap >= 2 && tape_len >= 0, "marl_rollout_closed: path_cap=%d tape_len=%d", path_cap, tape_len);
+    MARL_REQUIRE(d_map_id || M >= B, "marl_rollout_closed: map_id is NULL but M < B");
+    MARL_REQUIRE(!d_wf_n || (d_wf_mean && d_wf_S && d_wf_std), "marl_rollout_closed: partial Welford state");
+    RolloutArgs r = {};
+    r.B = B; r.T = T; r.t0 = t0; r.K = K;
+    r.p_state = d_p_state; r.e_tape = nullptr; r.action_tape = d_action_tape; r.seed = seed;
+    r.grid_bits = d_grid_bits; r.raser_bits = d_raser_bits; r.map_id = d_map_id; r.action_table = d_action_table;
+    r.wf_n = (long long *)d_wf_n; r.wf_mean = d_wf_mean; r.wf_S = d_wf_S; r.wf_std = d_wf_std;
+    r.collision = d_collision; r.time_step = d_time_step; r.rec = *rec;
+    r.e_state = d_e_state; r.target = d_target; r.path = d_path; r.path_len = d_path_len; r.path_cap = path_cap;
+    r.tape_len = tape_len; r.inflated_bits = d_inflated_bits; r.target_tape = d_target_tape; r.tape_pos = d_tape_pos;
+    r.ev_status = d_evader_status;
+    return launch_rollout(c, r, true, (cudaStream_t)stream);
 }

@@ -232,16 +232,56 @@ class BatchedPursuitEnv:
         if sync_evader:
             self.e_state.copy_(e_tape[K])
 
-    def rollout_closed(self, arena, K, t0=0, action_tape=None, seed=0):
-        """K closed-loop env iterations with the A* evader on the GPU: per iteration one evader launch (writes the
-        before/after evader states) and one fused observe/step/reward-norm/store launch.  Nothing touches the host,
-        so the whole sequence can be captured in a CUDA graph (see EpisodeGraph)."""
-        if getattr(self, "_e_tape2", None) is None:
-            self._e_tape2 = torch.zeros(2, self.B, 4, dtype=torch.float64, device=self.device)
-        for k in range(K):
-            self.evader_step(self._e_tape2)
-            self.rollout(arena, 1, t0 + k, e_tape=self._e_tape2,
-                         action_tape=None if action_tape is None else action_tape[k:k + 1], seed=seed, sync_evader=False)
+    def evader_replan(self):
+        """Evader.replan for every env whose time_step is a multiple of `difficulty` (others untouched)."""
+        _lib.check(self.lib.marl_evader_replan(
+            self._pp(), self.B, self.M, _lib.ptr(self.e_state), _lib.ptr(self.p_state), _lib.ptr(self.target),
+            _lib.ptr(self.path), _lib.ptr(self.path_len), self.PATH_CAP, _lib.ptr(self.time_step),
+            _lib.ptr(self.grid_bits), _lib.ptr(self.map_id), _lib.ptr(self.evader_status), _lib.stream_ptr()),
+            "marl_evader_replan")
+        self.launches += 1
+
+    def rollout_closed(self, arena, K, t0=0, action_tape=None, seed=0, env_t0=0, timers=None):
+        """K closed-loop env iterations with the A* evader on the GPU.  The evader's per-step move is fused into the
+        rollout kernel; replanning is one launch per `difficulty` steps, so an episode of T steps is
+        2*ceil(T/difficulty) launches.  `env_t0` is the (lock-step) env time_step at entry.  Nothing touches the host,
+        so the whole sequence can be captured in a CUDA graph (EpisodeGraph).
+        timers: optional dict name -> list of (start_event, end_event) filled around every launch (profiling aid)."""
+        import ctypes
+        rec = arena.records()
+        D = self.params.difficulty
+
+        def mark(name):
+            if timers is None:
+                return None
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            timers.setdefault(name, []).append(ev)
+            ev[0].record()
+            return ev
+
+        k = 0
+        while k < K:
+            ts = env_t0 + k
+            if ts % D == 0:
+                ev = mark("evader_kernel(replan)")
+                self.evader_replan()
+                if ev:
+                    ev[1].record()
+            chunk = min(D - ts % D, K - k)
+            tape = None if action_tape is None else action_tape[k:k + chunk]
+            ev = mark("rollout_kernel(closed)")
+            _lib.check(self.lib.marl_rollout_closed(
+                self._pp(), self.B, self.M, arena.T, t0 + k, chunk, _lib.ptr(self.p_state), _lib.ptr(self.e_state),
+                _lib.ptr(self.target), _lib.ptr(self.path), _lib.ptr(self.path_len), self.PATH_CAP,
+                _lib.ptr(self.inflated_bits), _lib.ptr(self.target_tape), self._tape_len, _lib.ptr(self.tape_pos),
+                _lib.ptr(self.evader_status), _lib.ptr(tape), ctypes.c_uint64(seed), _lib.ptr(self.grid_bits),
+                _lib.ptr(self.raser_bits), _lib.ptr(self.map_id), _lib.ptr(self.action_table), _lib.ptr(self.wf_n),
+                _lib.ptr(self.wf_mean), _lib.ptr(self.wf_S), _lib.ptr(self.wf_std), _lib.ptr(self.collision),
+                _lib.ptr(self.time_step), ctypes.byref(rec), _lib.stream_ptr()), "marl_rollout_closed")
+            if ev:
+                ev[1].record()
+            self.launches += 1
+            k += chunk
 
     def snapshot(self):
         """Device-side copy of everything an episode mutates (for replaying identical episodes)."""
@@ -255,8 +295,8 @@ class BatchedPursuitEnv:
 
 
 class EpisodeGraph:
-    """One whole closed-loop episode (T env steps = 2T kernel launches) captured in a CUDA graph: the rollout inner
-    loop is launch-bound at 4096 envs, so the graph removes ~2T host launch latencies per episode."""
+    """One whole closed-loop episode (2*ceil(T/difficulty) kernel launches) captured in a CUDA graph, so replaying
+    an episode costs one host call."""
 
     def __init__(self, env, arena, T, seed=0):
         self.env, self.arena, self.T = env, arena, T
@@ -273,7 +313,8 @@ class EpisodeGraph:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         env.restore(snap)
-        self.launches_per_replay = 2 * T
+        D = env.params.difficulty
+        self.launches_per_replay = 2 * ((T + D - 1) // D)
 
     def replay(self):
         self.graph.replay()

@@ -113,6 +113,7 @@ int marl_raser_map_build(const marl_env_params *p, int32_t M, const uint32_t *d_
 #define MARL_EV_HEAP_OVERFLOW 1
 #define MARL_EV_PATH_OVERFLOW 2
 #define MARL_EV_TAPE_EXHAUSTED 4
+#define MARL_EV_MISSED_REPLAN 8   /* marl_rollout_closed stepped across a replanning boundary */
 int marl_evader_step(const marl_env_params *p, int32_t B, int32_t M,
                      double *d_e_state, const double *d_p_state, int32_t *d_target,
                      int16_t *d_path, int32_t *d_path_len, int32_t path_cap,
@@ -120,6 +121,14 @@ int marl_evader_step(const marl_env_params *p, int32_t B, int32_t M,
                      const uint32_t *d_grid_bits, const uint32_t *d_inflated_bits, const int32_t *d_map_id,
                      const int32_t *d_target_tape, int32_t tape_len, int32_t *d_tape_pos,
                      int32_t *d_status, double *d_e_tape2, void *stream);
+
+/* Replanning only (Evader.replan, agent.py:232-259) for the envs with time_step % difficulty == 0; the others
+ * return immediately.  Used by the chunked closed-loop rollout: one replan launch per `difficulty` steps, the
+ * per-step move being fused into marl_rollout_closed. */
+int marl_evader_replan(const marl_env_params *p, int32_t B, int32_t M, const double *d_e_state,
+                       const double *d_p_state, const int32_t *d_target, int16_t *d_path, int32_t *d_path_len,
+                       int32_t path_cap, const int32_t *d_time_step, const uint32_t *d_grid_bits,
+                       const int32_t *d_map_id, int32_t *d_status, void *stream);
 
 /* ---- kernel 3a: Welford reward normalisation -----------------------------------------------------
  * Replaces Normalization.__call__ / RunningMeanStd.update (DHGN/normalization.py:4-35) applied per env:
@@ -177,6 +186,21 @@ int marl_rollout_steps(const marl_env_params *p, int32_t B, int32_t M, int32_t T
                        int64_t *d_wf_n, double *d_wf_mean, double *d_wf_S, double *d_wf_std,
                        uint8_t *d_collision, int32_t *d_time_step,
                        const marl_rollout_records *rec, void *stream);
+
+/* Closed-loop variant: the evader is simulated on the device.  K <= difficulty consecutive iterations of
+ * observe -> attacker_step's move (waypoint following, dynamics, target resampling from the tape) -> step ->
+ * reward-norm -> store; the caller launches marl_evader_replan before every chunk that starts on a replanning
+ * boundary (time_step % difficulty == 0).  Evader state arguments as in marl_evader_step. */
+int marl_rollout_closed(const marl_env_params *p, int32_t B, int32_t M, int32_t T, int32_t t0, int32_t K,
+                        double *d_p_state, double *d_e_state, int32_t *d_target, const int16_t *d_path,
+                        int32_t *d_path_len, int32_t path_cap, const uint32_t *d_inflated_bits,
+                        const int32_t *d_target_tape, int32_t tape_len, int32_t *d_tape_pos,
+                        int32_t *d_evader_status, const int32_t *d_action_tape, uint64_t seed,
+                        const uint32_t *d_grid_bits, const uint32_t *d_raser_bits, const int32_t *d_map_id,
+                        const double *d_action_table,
+                        int64_t *d_wf_n, double *d_wf_mean, double *d_wf_S, double *d_wf_std,
+                        uint8_t *d_collision, int32_t *d_time_step,
+                        const marl_rollout_records *rec, void *stream);
 
 #ifdef __cplusplus
 }

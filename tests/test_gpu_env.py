@@ -329,3 +329,58 @@ def test_stepwise_kernels_equal_fused_rollout_at_full_size():
     low = np.tril(np.ones((N, N), bool), -1)
     low[:, 1] = False
     assert not adj[:, low].any()
+
+
+def test_closed_loop_rollout_vs_oracle(oracle):
+    """Whole closed loop on the GPU (A* replanning + fused evader move + env kernels) against the oracle's closed
+    loop.  Discrete records exact; the evader's fp64 state differs only by libm ulps."""
+    from distributed_multi_agent_reinforcement_learning_b200 import default_config, maps
+    from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import RolloutArena
+    import bench
+    B, N, M, K = 96, 8, 12, 45
+    cfg = default_config(env__num_defender=N, env__max_steps=K)
+    wl = bench.host_workload(cfg, B, M, seed=21)
+    from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv
+    env = BatchedPursuitEnv(cfg, B, num_maps=M)
+    env.set_maps(wl["grids"], wl["inflated"])
+    env.set_state(wl["p_state"], wl["e_state"], wl["target"], wl["map_id"], time_step=0)
+    env.set_target_tape(wl["tape"])
+    env.start_episode()
+    actions = _rand_actions_numpy(99, B, N, 0, K)
+    # oracle
+    p = oracle.EnvParams.from_dict(env.params.as_dict())
+    O = env.O
+    st = dict(p_state=wl["p_state"].copy(), e_state=wl["e_state"].copy(), target=wl["target"].copy(),
+              path=np.zeros((B, 512, 2), np.int16), path_len=np.zeros(B, np.int32),
+              grid=np.ascontiguousarray(wl["grids"]), inflated=np.ascontiguousarray(wl["inflated"]),
+              raser=np.ascontiguousarray(maps.unpack_words(env.raser_bits.cpu().numpy(), O).reshape(M, p.W * p.H, O)),
+              ob_count=np.minimum(env.boundary_count.cpu().numpy(), O).astype(np.int32), map_id=wl["map_id"].copy(),
+              action_table=env.action_table.cpu().numpy().copy(), tape=np.ascontiguousarray(wl["tape"]),
+              tape_pos=np.zeros(B, np.int32), p_adj=np.zeros((B, N, N), np.uint8), o_adj=np.zeros((B, N, O), np.uint8),
+              e_adj=np.zeros((B, N), np.uint8), reward=np.zeros((B, N), np.int32), can_apply=np.zeros((B, N), np.uint8),
+              collision=np.zeros(B, np.uint8), time_step=np.zeros(B, np.int32), done=np.zeros(B, np.uint8),
+              wf_n=np.zeros(B, np.int64), wf_mean=np.zeros((B, N)), wf_S=np.zeros((B, N)), wf_std=np.zeros((B, N)),
+              r_norm=np.zeros((B, N), np.float32), status=np.zeros(B, np.int32))
+    rec = dict(reward=[], e_adj=[], o_adj=[], p_adj=[], e_before=[])
+    for k in range(K):
+        st["action"] = np.ascontiguousarray(actions[k])
+        rec["e_before"].append(st["e_state"].copy())
+        oracle.rollout_iteration_closed(p, st)
+        for key in ("reward", "e_adj", "o_adj", "p_adj"):
+            rec[key].append(st[key].copy())
+    assert not st["status"].any()
+    arena = RolloutArena(env.params, B, K, env.device)
+    env.rollout_closed(arena, K, 0, action_tape=torch.from_numpy(actions).cuda())
+    torch.cuda.synchronize()
+    assert int(env.evader_status.max().item()) == 0
+    assert np.array_equal(env.path_len.cpu().numpy(), st["path_len"])
+    assert np.array_equal(env.target.cpu().numpy(), st["target"])
+    assert np.array_equal(env.tape_pos.cpu().numpy(), st["tape_pos"])
+    np.testing.assert_allclose(env.e_state.cpu().numpy(), st["e_state"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(arena.e_state_f32.cpu().numpy()[:, :, 0], np.stack(rec["e_before"]).astype(np.float32), rtol=1e-6)
+    assert np.array_equal(arena.raw_reward.cpu().numpy(), np.stack(rec["reward"]))
+    assert np.array_equal(arena.e_adj.cpu().numpy(), np.stack(rec["e_adj"]))
+    assert np.array_equal(maps.unpack_words(arena.o_adj_bits.cpu().numpy(), O), np.stack(rec["o_adj"]))
+    assert np.array_equal(maps.unpack_words(arena.p_adj_bits.cpu().numpy(), N), np.stack(rec["p_adj"]))
+    assert np.array_equal(_bits(env.p_state.cpu().numpy()), _bits(st["p_state"]))
+    assert (env.time_step == K).all()
