@@ -14,6 +14,7 @@
 namespace marl {
 
 static constexpr int kOpenCap = 1536;
+static constexpr int kPopBudget = 192;   // pops before the reachability check (p99 of successful searches is ~200)
 
 struct EvaderArgs {
     int B, path_cap, tape_len;
@@ -62,7 +63,7 @@ __device__ __forceinline__ SearchSmem carve(unsigned char *smem, int W1, int NOD
     s.of = s.g + NODES;
     s.mov = reinterpret_cast<uint64_t *>(s.of + kOpenCap);
     s.blk = s.mov + W1;
-    s.par = reinterpret_cast<uint16_t *>(s.blk + W1);
+    s.par = reinterpret_cast<uint16_t *>(s.blk + 2 * W1);   // [blk][reach]
     s.on = s.par + ((NODES + 3) & ~3);
     return s;
 }
@@ -70,7 +71,36 @@ __device__ __forceinline__ SearchSmem carve(unsigned char *smem, int W1, int NOD
 static size_t search_smem_bytes(const EnvDev &c)
 {
     const int W1 = c.W + 1, H1 = c.H + 1, NODES = W1 * H1;
-    return sizeof(double) * (NODES + kOpenCap) + sizeof(uint64_t) * 2 * W1 + sizeof(uint16_t) * (((NODES + 3) & ~3) + kOpenCap);
+    return sizeof(double) * (NODES + kOpenCap) + sizeof(uint64_t) * 3 * W1 + sizeof(uint16_t) * (((NODES + 3) & ~3) + kOpenCap);
+}
+
+// Is `goal` reachable from `start` through unblocked nodes of the [0,W]x[0,H] lattice with 8-connected moves?
+// Bit-parallel flood fill on the 64-bit columns (one lane per column, in-place monotone OR until the fixed point).
+// Used to cut the search short: when the goal is unreachable the reference's A* exhausts the whole component and
+// returns [s_start] (astar.py:67-71) — the same answer this gives after a few thousand cycles.
+__device__ bool goal_reachable(const SearchSmem &sm, uint64_t *reach, int W1, int H1, int sx, int sy, int gx, int gy)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t dom = (H1 >= 64) ? ~0ull : ((1ull << H1) - 1ull);
+    for (int x = lane; x < W1; x += 32) reach[x] = 0ull;
+    __syncwarp();
+    if (lane == 0) reach[sx] = (1ull << sy) & ~sm.blk[sx];
+    __syncwarp();
+    for (;;) {
+        bool changed = false;
+        for (int x = lane; x < W1; x += 32) {
+            const uint64_t c = reach[x];
+            uint64_t nb = c;
+            if (x > 0) nb |= reach[x - 1];
+            if (x + 1 < W1) nb |= reach[x + 1];
+            nb |= (nb << 1) | (nb >> 1);
+            const uint64_t nw = (c | nb) & ~sm.blk[x] & dom;
+            if (nw != c) { reach[x] = nw; changed = true; }
+        }
+        __syncwarp();
+        if ((reach[gx] >> gy) & 1ull) return true;
+        if (!__any_sync(0xffffffffu, changed)) return false;
+    }
 }
 
 // Evader.replan (agent.py:232-259) for one env by one warp.  Returns the new path length (uniform across lanes);
@@ -130,10 +160,13 @@ __device__ int replan_warp(const EnvDev &c, const SearchSmem &sm, const uint32_t
                 sm.of[0] = 0.0 + 2.5 * (double)(abs(tx - cx) + abs(ty - cy));
                 sm.on[0] = (uint16_t)start;
             }
-            int n_open = 1;
+            int n_open = 1, pops = 0;
             __syncwarp();
             bool reached = false;
             while (n_open > 0) {
+                if (++pops == kPopBudget) {   // long search: make sure it can succeed before spending more on it
+                    if (!goal_reachable(sm, sm.blk + W1, W1, H1, cx, cy, tx, ty)) break;
+                }
                 // ---- pop: warp-wide arg-min of (f, node) over the unsorted OPEN array ----
                 unsigned long long best = ~0ull;
                 int best_node = 0x7fffffff, best_idx = -1;

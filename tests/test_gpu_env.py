@@ -384,3 +384,47 @@ def test_closed_loop_rollout_vs_oracle(oracle):
     assert np.array_equal(maps.unpack_words(arena.p_adj_bits.cpu().numpy(), N), np.stack(rec["p_adj"]))
     assert np.array_equal(_bits(env.p_state.cpu().numpy()), _bits(st["p_state"]))
     assert (env.time_step == K).all()
+
+
+def test_evader_hard_searches_vs_oracle(oracle):
+    """Searches that run past the reachability-check budget: (a) goal sealed inside a ring of obstacles — the reference's
+    A* exhausts the component and returns [start]; (b) a serpentine maze with a long but existing path."""
+    from distributed_multi_agent_reinforcement_learning_b200 import default_config, maps
+    from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv
+    cfg = default_config(env__num_defender=4)
+    W, H = cfg.map.map_size
+    ring = np.zeros((W, H), np.uint8)
+    ring[36:47, 26] = ring[36:47, 36] = 1
+    ring[36, 26:37] = ring[46, 26:37] = 1                   # closed ring around (41, 31)
+    maze = np.zeros((W, H), np.uint8)
+    for i, x in enumerate(range(8, 52, 6)):                  # walls with alternating gaps
+        if i % 2 == 0:
+            maze[x, 0:H - 6] = 1
+        else:
+            maze[x, 6:H] = 1
+    grids = np.stack([ring, maze])
+    B = 2
+    env = BatchedPursuitEnv(cfg, B, num_maps=2)
+    env.set_maps(grids)
+    p_state = np.zeros((B, 4, 4))
+    p_state[:, :, 0] = [[2, 3, 4, 5]] * B                    # pursuers parked out of the way
+    p_state[:, :, 1] = 50.0
+    e_state = np.array([[5.2, 5.1, 0, 0], [2.3, 2.2, 0, 0]], np.float64)
+    target = np.array([[41, 31], [57, 3]], np.int32)
+    env.set_state(p_state, e_state, target, np.arange(B), time_step=0)
+    env.start_episode()
+    env.set_target_tape(np.zeros((B, 0, 2), np.int32))
+    env.evader_step()
+    torch.cuda.synchronize()
+    assert not (env.evader_status.cpu().numpy() & 3).any()
+    p = oracle.EnvParams.from_dict(env.params.as_dict())
+    infl = maps.dilate(grids, 2)
+    for b in range(B):
+        ev = oracle.EvaderState(e_state[b], target[b])
+        assert oracle.evader_step(p, ev, p_state[b], 0, grids[b], infl[b], np.zeros((0, 2), np.int32)) in (0, -2)
+        L = ev.path_len.value
+        assert int(env.path_len[b]) == L, (b, int(env.path_len[b]), L)
+        assert np.array_equal(env.path[b, :L].cpu().numpy(), ev.path[:L])
+        np.testing.assert_allclose(env.e_state[b].cpu().numpy(), ev.e_state, rtol=1e-9, atol=1e-9)
+    assert int(env.path_len[0]) == 1                          # sealed goal -> [start]
+    assert int(env.path_len[1]) > 150                         # the maze path is long
