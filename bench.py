@@ -30,6 +30,7 @@ if ROOT not in sys.path:
 METRIC = "agent_env_steps_per_sec"
 UNIT = "agent-env-steps/s"
 N_AGENTS, B_PER_GPU, T_STEPS, N_MAPS = 8, 4096, 150, 256
+STREAM_GROUPS = 16   # independent env sub-batches on separate streams inside the episode graph
 SURVEY_BYTES_PER_AGENT_STEP = 118.0   # 72 state r/w + 22 raser row + 1 p_adj + 1 e_adj + 22 o_adj (N=8, O=176)
 
 
@@ -39,7 +40,7 @@ def workload_config(n_gpus):
             "map_pool_per_gpu": N_MAPS, "evader": "gpu A* (replan every 10 steps)",
             "policy": "uniform random actions from a device counter RNG (network not in the loop this round)",
             "parallelism": f"dp{n_gpus} (independent env shards, no data-path collective)",
-            "l2": "flushed between timed iterations (256 MiB write)"}
+            "stream_groups": STREAM_GROUPS, "l2": "flushed between timed iterations (256 MiB write)"}
 
 
 def make_cfg():
@@ -211,7 +212,7 @@ def run_ours(args):
     env.start_episode()
     arena = RolloutArena(env.params, B, T, dev)
     snap = env.snapshot()
-    graph = EpisodeGraph(env, arena, T, seed=0xB200 + rank)
+    graph = EpisodeGraph(env, arena, T, seed=0xB200 + rank, groups=STREAM_GROUPS)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():

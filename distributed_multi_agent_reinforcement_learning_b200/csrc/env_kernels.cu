@@ -215,6 +215,8 @@ env_observe_kernel(EnvDev c, int B, const double *__restrict__ p_state, const do
 // ---- fused env-only rollout ------------------------------------------------------------------------------
 struct RolloutArgs {
     int B, T, t0, K;
+    int env0;                    // global index of this sub-batch's first env (keys the action generator)
+    int B_stride;                // envs per time slab of the arena (>= B; == B unless a sub-batch is being rolled)
     double *p_state;             // [B,N,4] in/out
     const double *e_tape;        // [K+1,B,4]
     const int32_t *action_tape;  // [K,B,N] or null
@@ -295,7 +297,7 @@ rollout_kernel(EnvDev c, RolloutArgs r)
     double2 *s_raw = s_tiles + (warp * 2 + 0) * 32 * APL + g.sub * Gp::SLOTS;
     double2 *s_fin = s_tiles + (warp * 2 + 1) * 32 * APL + g.sub * Gp::SLOTS;
     uint32_t *s_words = s_words_all + (size_t)warp * (32 * APL) * (c.OW + c.NW);
-    const int64_t BN = (int64_t)B * N;
+    const int64_t BN = (int64_t)B * N, BN_rec = (int64_t)r.B_stride * N;
     double2 e_cur = make_double2(0.0, 0.0), e_vel = make_double2(0.0, 0.0);
     const double *e_src = CLOSED ? r.e_state : r.e_tape;
     if (env_ok) {
@@ -315,7 +317,7 @@ rollout_kernel(EnvDev c, RolloutArgs r)
     }
     for (int k = 0; k < r.K; ++k) {
         const int t = r.t0 + k;
-        const int64_t tb = (int64_t)t * BN;   // time-major record offset in agents
+        const int64_t tb = (int64_t)t * BN_rec;   // time-major record offset in agents
         // prefetch the evader state after this iteration's attacker_step and the actions (independent of observe)
         double2 e_nxt = e_cur, e_nvel = e_vel;
         int act[APL];
@@ -343,7 +345,7 @@ rollout_kernel(EnvDev c, RolloutArgs r)
             act[a] = 8;
             if (env_ok && i < N) {
                 const int64_t idx = g.env * N + i;
-                act[a] = r.action_tape ? r.action_tape[(int64_t)k * BN + idx] : rand_action(r.seed, idx, t);
+                act[a] = r.action_tape ? r.action_tape[(int64_t)k * BN_rec + idx] : rand_action(r.seed, idx + (int64_t)r.env0 * N, t);
             }
         }
         // -- observe (state before the step, evader before attacker_step): mappo_parallel.py:759-763
@@ -372,7 +374,7 @@ rollout_kernel(EnvDev c, RolloutArgs r)
             }
         }
         if (env_ok && g.gl == 0 && r.rec.e_state_f32)
-            *reinterpret_cast<float4 *>(r.rec.e_state_f32 + ((int64_t)t * B + g.env) * 4) =
+            *reinterpret_cast<float4 *>(r.rec.e_state_f32 + ((int64_t)t * r.B_stride + g.env) * 4) =
                 make_float4((float)e_cur.x, (float)e_cur.y, (float)e_vel.x, (float)e_vel.y);
         // -- step against the evader state AFTER attacker_step: mappo_parallel.py:765,793
         int rew[APL];
@@ -532,7 +534,7 @@ extern "C" int marl_rollout_steps(const marl_env_params *p, int32_t B, int32_t M
     MARL_REQUIRE(d_map_id || M >= B, "marl_rollout_steps: map_id is NULL but M < B");
     MARL_REQUIRE(!d_wf_n || (d_wf_mean && d_wf_S && d_wf_std), "marl_rollout_steps: partial Welford state");
     RolloutArgs r = {};
-    r.B = B; r.T = T; r.t0 = t0; r.K = K;
+    r.B = B; r.T = T; r.t0 = t0; r.K = K; r.B_stride = B;
     r.p_state = d_p_state; r.e_tape = d_e_tape; r.action_tape = d_action_tape; r.seed = seed;
     r.grid_bits = d_grid_bits; r.raser_bits = d_raser_bits; r.map_id = d_map_id; r.action_table = d_action_table;
     r.wf_n = (long long *)d_wf_n; r.wf_mean = d_wf_mean; r.wf_S = d_wf_S; r.wf_std = d_wf_std;
@@ -540,8 +542,8 @@ extern "C" int marl_rollout_steps(const marl_env_params *p, int32_t B, int32_t M
     return launch_rollout(c, r, false, (cudaStream_t)stream);
 }
 
-extern "C" int marl_rollout_closed(const marl_env_params *p, int32_t B, int32_t M, int32_t T, int32_t t0, int32_t K,
-                                   double *d_p_state, double *d_e_state, int32_t *d_target, const int16_t *d_path,
+extern "C" int marl_rollout_closed(const marl_env_params *p, int32_t B, int32_t B_stride, int32_t env0, int32_t M, int32_t T,
+                                   int32_t t0, int32_t K, double *d_p_state, double *d_e_state, int32_t *d_target, const int16_t *d_path,
                                    int32_t *d_path_len, int32_t path_cap, const uint32_t *d_inflated_bits,
                                    const int32_t *d_target_tape, int32_t tape_len, int32_t *d_tape_pos,
                                    int32_t *d_evader_status, const int32_t *d_action_tape, uint64_t seed,
@@ -554,6 +556,7 @@ extern "C" int marl_rollout_closed(const marl_env_params *p, int32_t B, int32_t 
     int rc = make_env_dev(p, &c);
     if (rc) return rc;
     MARL_REQUIRE(B > 0 && M > 0 && K > 0 && t0 >= 0 && t0 + K <= T, "marl_rollout_closed: B=%d M=%d T=%d t0=%d K=%d", B, M, T, t0, K);
+    MARL_REQUIRE((B_stride == 0 && env0 == 0) || (B_stride >= env0 + B && env0 >= 0), "marl_rollout_closed: B_stride=%d env0=%d B=%d", B_stride, env0, B);
     MARL_REQUIRE(K <= c.difficulty, "marl_rollout_closed: K=%d crosses a replanning boundary (difficulty=%d)", K, c.difficulty);
     MARL_REQUIRE(d_p_state && d_e_state && d_target && d_path && d_path_len && d_inflated_bits && d_tape_pos &&
                      (d_target_tape || tape_len == 0) && d_grid_bits && d_raser_bits && d_action_table && d_time_step && rec,
@@ -562,7 +565,7 @@ extern "C" int marl_rollout_closed(const marl_env_params *p, int32_t B, int32_t 
     MARL_REQUIRE(d_map_id || M >= B, "marl_rollout_closed: map_id is NULL but M < B");
     MARL_REQUIRE(!d_wf_n || (d_wf_mean && d_wf_S && d_wf_std), "marl_rollout_closed: partial Welford state");
     RolloutArgs r = {};
-    r.B = B; r.T = T; r.t0 = t0; r.K = K;
+    r.B = B; r.T = T; r.t0 = t0; r.K = K; r.B_stride = B_stride > 0 ? B_stride : B; r.env0 = env0;
     r.p_state = d_p_state; r.e_tape = nullptr; r.action_tape = d_action_tape; r.seed = seed;
     r.grid_bits = d_grid_bits; r.raser_bits = d_raser_bits; r.map_id = d_map_id; r.action_table = d_action_table;
     r.wf_n = (long long *)d_wf_n; r.wf_mean = d_wf_mean; r.wf_S = d_wf_S; r.wf_std = d_wf_std;

@@ -232,56 +232,95 @@ class BatchedPursuitEnv:
         if sync_evader:
             self.e_state.copy_(e_tape[K])
 
-    def evader_replan(self):
-        """Evader.replan for every env whose time_step is a multiple of `difficulty` (others untouched)."""
+    def evader_replan(self, lo=0, hi=None, stream=None):
+        """Evader.replan for every env in [lo, hi) whose time_step is a multiple of `difficulty`."""
+        hi = self.B if hi is None else hi
+        sl = slice(lo, hi)
         _lib.check(self.lib.marl_evader_replan(
-            self._pp(), self.B, self.M, _lib.ptr(self.e_state), _lib.ptr(self.p_state), _lib.ptr(self.target),
-            _lib.ptr(self.path), _lib.ptr(self.path_len), self.PATH_CAP, _lib.ptr(self.time_step),
-            _lib.ptr(self.grid_bits), _lib.ptr(self.map_id), _lib.ptr(self.evader_status), _lib.stream_ptr()),
-            "marl_evader_replan")
+            self._pp(), hi - lo, self.M, _lib.ptr(self.e_state[sl]), _lib.ptr(self.p_state[sl]),
+            _lib.ptr(self.target[sl]), _lib.ptr(self.path[sl]), _lib.ptr(self.path_len[sl]), self.PATH_CAP,
+            _lib.ptr(self.time_step[sl]), _lib.ptr(self.grid_bits), _lib.ptr(self.map_id[sl]),
+            _lib.ptr(self.evader_status[sl]), _lib.stream_ptr(stream)), "marl_evader_replan")
         self.launches += 1
 
-    def rollout_closed(self, arena, K, t0=0, action_tape=None, seed=0, env_t0=0, timers=None):
-        """K closed-loop env iterations with the A* evader on the GPU.  The evader's per-step move is fused into the
-        rollout kernel; replanning is one launch per `difficulty` steps, so an episode of T steps is
-        2*ceil(T/difficulty) launches.  `env_t0` is the (lock-step) env time_step at entry.  Nothing touches the host,
-        so the whole sequence can be captured in a CUDA graph (EpisodeGraph).
-        timers: optional dict name -> list of (start_event, end_event) filled around every launch (profiling aid)."""
+    def _closed_chunk(self, arena, rec_ptrs, lo, hi, t, chunk, action_tape, k, seed, stream):
+        """One marl_rollout_closed launch for envs [lo, hi) and arena time index t."""
         import ctypes
-        rec = arena.records()
+        sl = slice(lo, hi)
+        rec = _lib.RolloutRecords()
+        for f, (base, row_bytes) in rec_ptrs.items():
+            setattr(rec, f, None if base is None else base + lo * row_bytes)
+        tape = None
+        if action_tape is not None:
+            tape = action_tape[k].data_ptr() + lo * self.N * 4      # [K,B,N] int32, env-offset, B_stride time stride
+        _lib.check(self.lib.marl_rollout_closed(
+            self._pp(), hi - lo, self.B, lo, self.M, arena.T, t, chunk, _lib.ptr(self.p_state[sl]),
+            _lib.ptr(self.e_state[sl]), _lib.ptr(self.target[sl]), _lib.ptr(self.path[sl]), _lib.ptr(self.path_len[sl]),
+            self.PATH_CAP, _lib.ptr(self.inflated_bits), _lib.ptr(self.target_tape[sl]), self._tape_len,
+            _lib.ptr(self.tape_pos[sl]), _lib.ptr(self.evader_status[sl]), tape, ctypes.c_uint64(seed),
+            _lib.ptr(self.grid_bits), _lib.ptr(self.raser_bits), _lib.ptr(self.map_id[sl]), _lib.ptr(self.action_table),
+            _lib.ptr(self.wf_n[sl]), _lib.ptr(self.wf_mean[sl]), _lib.ptr(self.wf_S[sl]), _lib.ptr(self.wf_std[sl]),
+            _lib.ptr(self.collision[sl]), _lib.ptr(self.time_step[sl]), ctypes.byref(rec), _lib.stream_ptr(stream)),
+            "marl_rollout_closed")
+        self.launches += 1
+
+    def rollout_closed(self, arena, K, t0=0, action_tape=None, seed=0, env_t0=0, timers=None, groups=1):
+        """K closed-loop env iterations with the A* evader on the GPU.  The evader's per-step move is fused into the
+        rollout kernel; replanning is one launch per `difficulty` steps, so K steps are 2*ceil(K/difficulty) launches
+        per group.  `env_t0` is the (lock-step) env time_step at entry.
+
+        groups > 1 splits the envs into that many contiguous sub-batches, each running its own launch chain on its own
+        CUDA stream: a search that takes 100x longer than the median (A* is a long-tailed workload) then only holds
+        up its own sub-batch while the other chains keep the SMs busy.  Results are identical for any grouping.
+        Nothing touches the host, so the whole thing can be captured in a CUDA graph (EpisodeGraph).
+        timers: optional dict name -> list of (start_event, end_event) around every launch (groups == 1 only)."""
+        assert arena.B == self.B
+        if action_tape is not None:
+            assert tuple(action_tape.shape) == (K, self.B, self.N) and action_tape.dtype == torch.int32
+            assert action_tape.is_contiguous()
         D = self.params.difficulty
+        rec_ptrs = arena.record_pointers()
+        groups = max(1, min(int(groups), self.B))
+        bounds = [(g * self.B // groups, (g + 1) * self.B // groups) for g in range(groups)]
 
         def mark(name):
-            if timers is None:
+            if timers is None or groups != 1:
                 return None
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             timers.setdefault(name, []).append(ev)
             ev[0].record()
             return ev
 
-        k = 0
-        while k < K:
-            ts = env_t0 + k
-            if ts % D == 0:
-                ev = mark("evader_kernel(replan)")
-                self.evader_replan()
+        def chain(lo, hi, stream):
+            k = 0
+            while k < K:
+                ts = env_t0 + k
+                if ts % D == 0:
+                    ev = mark("evader_kernel(replan)")
+                    self.evader_replan(lo, hi, stream)
+                    if ev:
+                        ev[1].record()
+                chunk = min(D - ts % D, K - k)
+                ev = mark("rollout_kernel(closed)")
+                self._closed_chunk(arena, rec_ptrs, lo, hi, t0 + k, chunk, action_tape, k, seed, stream)
                 if ev:
                     ev[1].record()
-            chunk = min(D - ts % D, K - k)
-            tape = None if action_tape is None else action_tape[k:k + chunk]
-            ev = mark("rollout_kernel(closed)")
-            _lib.check(self.lib.marl_rollout_closed(
-                self._pp(), self.B, self.M, arena.T, t0 + k, chunk, _lib.ptr(self.p_state), _lib.ptr(self.e_state),
-                _lib.ptr(self.target), _lib.ptr(self.path), _lib.ptr(self.path_len), self.PATH_CAP,
-                _lib.ptr(self.inflated_bits), _lib.ptr(self.target_tape), self._tape_len, _lib.ptr(self.tape_pos),
-                _lib.ptr(self.evader_status), _lib.ptr(tape), ctypes.c_uint64(seed), _lib.ptr(self.grid_bits),
-                _lib.ptr(self.raser_bits), _lib.ptr(self.map_id), _lib.ptr(self.action_table), _lib.ptr(self.wf_n),
-                _lib.ptr(self.wf_mean), _lib.ptr(self.wf_S), _lib.ptr(self.wf_std), _lib.ptr(self.collision),
-                _lib.ptr(self.time_step), ctypes.byref(rec), _lib.stream_ptr()), "marl_rollout_closed")
-            if ev:
-                ev[1].record()
-            self.launches += 1
-            k += chunk
+                k += chunk
+
+        if groups == 1:
+            chain(0, self.B, None)
+            return
+        main = torch.cuda.current_stream()
+        if len(getattr(self, "_streams", [])) < groups:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(groups)]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for (lo, hi), st in zip(bounds, self._streams):
+            st.wait_event(fork)
+            chain(lo, hi, st)
+            done = torch.cuda.Event()
+            done.record(st)
+            main.wait_event(done)
 
     def snapshot(self):
         """Device-side copy of everything an episode mutates (for replaying identical episodes)."""
@@ -298,10 +337,10 @@ class EpisodeGraph:
     """One whole closed-loop episode (2*ceil(T/difficulty) kernel launches) captured in a CUDA graph, so replaying
     an episode costs one host call."""
 
-    def __init__(self, env, arena, T, seed=0):
-        self.env, self.arena, self.T = env, arena, T
+    def __init__(self, env, arena, T, seed=0, groups=1):
+        self.env, self.arena, self.T, self.groups = env, arena, T, groups
         snap = env.snapshot()
-        env.rollout_closed(arena, T, 0, seed=seed)          # eager warm-up (also sets kernel attributes)
+        env.rollout_closed(arena, T, 0, seed=seed, groups=groups)   # eager warm-up (also sets kernel attributes)
         torch.cuda.synchronize()
         env.restore(snap)
         self.graph = torch.cuda.CUDAGraph()
@@ -309,12 +348,12 @@ class EpisodeGraph:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             with torch.cuda.graph(self.graph, stream=side):
-                env.rollout_closed(arena, T, 0, seed=seed)
+                env.rollout_closed(arena, T, 0, seed=seed, groups=groups)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         env.restore(snap)
         D = env.params.difficulty
-        self.launches_per_replay = 2 * ((T + D - 1) // D)
+        self.launches_per_replay = 2 * ((T + D - 1) // D) * max(1, min(groups, env.B))
 
     def replay(self):
         self.graph.replay()
@@ -351,6 +390,14 @@ class RolloutArena:
             t = getattr(self, f)
             setattr(rec, f, t.data_ptr() if t is not None else None)
         return rec
+
+    def record_pointers(self):
+        """field -> (device base pointer or None, bytes per env row of one time slab)."""
+        out = {}
+        for f in _lib.RolloutRecords.FIELDS:
+            t = getattr(self, f)
+            out[f] = (None, 0) if t is None else (t.data_ptr(), t[0, 0].numel() * t.element_size())
+        return out
 
     def nbytes(self):
         return sum(getattr(self, f).numel() * getattr(self, f).element_size()

@@ -190,9 +190,13 @@ int marl_rollout_steps(const marl_env_params *p, int32_t B, int32_t M, int32_t T
 /* Closed-loop variant: the evader is simulated on the device.  K <= difficulty consecutive iterations of
  * observe -> attacker_step's move (waypoint following, dynamics, target resampling from the tape) -> step ->
  * reward-norm -> store; the caller launches marl_evader_replan before every chunk that starts on a replanning
- * boundary (time_step % difficulty == 0).  Evader state arguments as in marl_evader_step. */
-int marl_rollout_closed(const marl_env_params *p, int32_t B, int32_t M, int32_t T, int32_t t0, int32_t K,
-                        double *d_p_state, double *d_e_state, int32_t *d_target, const int16_t *d_path,
+ * boundary (time_step % difficulty == 0).  Evader state arguments as in marl_evader_step.
+ * Sub-batches: to roll envs [e0, e0+B) of an arena holding B_stride envs per time slab, pass every per-env pointer
+ * (record and action-tape pointers included) already offset to env e0, B_stride = the arena's env count (0 means B)
+ * and env0 = e0 (it keys the action generator so that sub-batching does not change the actions).  Independent
+ * sub-batches can then run on different streams, so one slow A* search only delays its own sub-batch. */
+int marl_rollout_closed(const marl_env_params *p, int32_t B, int32_t B_stride, int32_t env0, int32_t M, int32_t T, int32_t t0,
+                        int32_t K, double *d_p_state, double *d_e_state, int32_t *d_target, const int16_t *d_path,
                         int32_t *d_path_len, int32_t path_cap, const uint32_t *d_inflated_bits,
                         const int32_t *d_target_tape, int32_t tape_len, int32_t *d_tape_pos,
                         int32_t *d_evader_status, const int32_t *d_action_tape, uint64_t seed,

@@ -427,4 +427,50 @@ def test_evader_hard_searches_vs_oracle(oracle):
         assert np.array_equal(env.path[b, :L].cpu().numpy(), ev.path[:L])
         np.testing.assert_allclose(env.e_state[b].cpu().numpy(), ev.e_state, rtol=1e-9, atol=1e-9)
     assert int(env.path_len[0]) == 1                          # sealed goal -> [start]
-    assert int(env.path_len[1]) > 150                         # the maze path is long
+    assert int(env.path_len[1]) > 100                         # the maze path is long
+
+
+def test_grouped_multistream_rollout_is_identical():
+    """Sub-batches on separate streams (and inside a CUDA graph) give bit-identical arenas and final states."""
+    from distributed_multi_agent_reinforcement_learning_b200 import default_config
+    from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv, EpisodeGraph, RolloutArena
+    import bench
+    B, N, M, K = 203, 8, 16, 37
+    cfg = default_config(env__num_defender=N, env__max_steps=K)
+    wl = bench.host_workload(cfg, B, M, seed=5)
+    env = BatchedPursuitEnv(cfg, B, num_maps=M)
+    env.set_maps(wl["grids"], wl["inflated"])
+    env.set_state(wl["p_state"], wl["e_state"], wl["target"], wl["map_id"], time_step=0)
+    env.set_target_tape(wl["tape"])
+    env.start_episode()
+    snap = env.snapshot()
+    fields = ("p_state_f32", "e_state_f32", "p_adj_bits", "e_adj", "o_adj_bits", "a_n", "r", "raw_reward")
+    a1 = RolloutArena(env.params, B, K, env.device)
+    env.rollout_closed(a1, K, 0, seed=7, groups=1)
+    torch.cuda.synchronize()
+    ref_state = {k: v.clone() for k, v in env.snapshot().items()}
+    for groups in (5, 16):
+        env.restore(snap)
+        a2 = RolloutArena(env.params, B, K, env.device)
+        env.rollout_closed(a2, K, 0, seed=7, groups=groups)
+        torch.cuda.synchronize()
+        for f in fields:
+            assert torch.equal(getattr(a1, f), getattr(a2, f)), (groups, f)
+        for k, v in env.snapshot().items():
+            assert torch.equal(v, ref_state[k]), (groups, k)
+    # with an action tape and through a captured graph
+    env.restore(snap)
+    tape = torch.from_numpy(_rand_actions_numpy(7, B, N, 0, K)).cuda()
+    a3 = RolloutArena(env.params, B, K, env.device)
+    env.rollout_closed(a3, K, 0, action_tape=tape, groups=4)
+    torch.cuda.synchronize()
+    for f in fields:
+        assert torch.equal(getattr(a1, f), getattr(a3, f)), f
+    env.restore(snap)
+    a4 = RolloutArena(env.params, B, K, env.device)
+    g = EpisodeGraph(env, a4, K, seed=7, groups=6)
+    a4.raw_reward.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for f in fields:
+        assert torch.equal(getattr(a1, f), getattr(a4, f)), f
