@@ -359,6 +359,10 @@ void orc_rescan(const marl_env_params *p, const uint8_t *grid, int e, const doub
 }
 
 /* agent.py:232-259 Evader.replan: try extend_dis, extend_dis-1, ..., 0; keep the first path with >= 2 nodes. */
+static _Thread_local int64_t orc_tl_pops = 0;   /* diagnostics: |CLOSED| summed over the searches of this thread */
+static int64_t *orc_pop_sink = NULL;            /* optional per-env accumulator set by orc_set_pop_sink */
+void orc_set_pop_sink(int64_t *sink) { orc_pop_sink = sink; }
+
 int32_t orc_replan(const marl_env_params *p, const uint8_t *grid, const double *e_state, const double *p_state,
                    const int32_t *target, int16_t *path, int32_t cap)
 {
@@ -367,7 +371,9 @@ int32_t orc_replan(const marl_env_params *p, const uint8_t *grid, const double *
     int32_t n = 1;
     for (int e = p->e_extend_dis; e >= 0; e--) {
         orc_rescan(p, grid, e, p_state, cx, cy, blocked);
-        n = orc_astar(p, blocked, cx, cy, target[0], target[1], path, cap, NULL);
+        int32_t nc = 0;
+        n = orc_astar(p, blocked, cx, cy, target[0], target[1], path, cap, &nc);
+        orc_tl_pops += nc;
         if (n >= 2 || n < 0) break;
     }
     free(blocked);
@@ -538,10 +544,12 @@ void orc_rollout_iteration_closed(const marl_env_params *p, int32_t B, double *p
             e_adj[(size_t)b * N + i] = (uint8_t)orc_find_attacker(p, g, orc_round(ps[4 * i]), orc_round(ps[4 * i + 1]),
                                                                  orc_round(es[0]), orc_round(es[1]));
         }
+        orc_tl_pops = 0;
         int32_t rc = orc_evader_step(p, es, ps, target + 2 * (size_t)b, path + (size_t)b * cap * 2, path_len + b, cap,
                                      time_step[b], g, inflated + (size_t)m * WH, tape + (size_t)b * tape_len * 2, tape_len,
                                      tape_pos + b);
         if (rc && status) status[b] = rc;
+        if (orc_pop_sink) orc_pop_sink[b] += orc_tl_pops;
         orc_env_step(p, ps, es, action + (size_t)b * N, g, action_table, reward + (size_t)b * N,
                      can_apply + (size_t)b * N, collision + b, time_step + b, done + b);
         orc_welford(N, reward + (size_t)b * N, wf_n + b, wf_mean + (size_t)b * N, wf_S + (size_t)b * N,
