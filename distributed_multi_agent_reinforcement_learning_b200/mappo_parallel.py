@@ -1,0 +1,554 @@
+"""MAPPO with the DHGN heterogeneous-graph encoder — B200 mirror of the reference `DHGN/mappo_parallel.py`.
+
+Same class names, constructor signatures, sub-module names (`shared_net`, `GRU`, `Mean`) and state_dict keys as the
+reference (`DHGN`, `SharedActor`, `SharedCritic`, `MAPPO`: DHGN/mappo_parallel.py:116-831), so checkpoints written by
+`torch.save(actor)` / `state_dict()` interchange (main.py:149-169, evaluator.py:329-330), and — because layers are
+created in the reference's order with the same torch initialisers — `torch.manual_seed(s); MAPPO(cfg, ...)` yields the
+reference's initial weights.
+
+The compute path is not the reference's: adjacency stays bit-packed, the three relations are message-passed and
+aggregated by one fused kernel, history averaging / GRU cells / heads+PPO loss / clip / Adam are our kernels
+(csrc/policy_kernels.cu via policy_ops.py); only the dense E-wide layers are library GEMMs.  The whole rollout for B
+envs runs on the GPU (`MAPPO.rollout_batched`); `explore_env(env, n)` keeps the reference's single-env signature.
+
+Reference quirks kept on purpose (parity is defined per phase):
+  * one encoder instance shared by actor and critic (:582-616); only `critic.Mean` is spectrally normalised (:485);
+  * rollout history: actor and critic datasets alias ONE list (:750-752), so both see [C(t-1), A(t-1), C(t-2), ...];
+  * critic "all ones" adjacency spans the O_b real boundary cells in rollout but all O padded slots in training;
+  * gradients accumulate over minibatches and clip_grad_norm_ acts on the running accumulation (:708-711);
+  * minibatches are sequential, unshuffled index ranges (:665).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.utils import spectral_norm
+
+from . import _lib, policy_ops as ops
+from .normalization import Normalization
+from .replay_buffer import BigBuffer, ReplayBuffer
+
+
+def orthogonal_init(layer, gain=1.0):
+    for name, param in layer.named_parameters():
+        if "bias" in name:
+            nn.init.constant_(param, 0)
+        elif "weight" in name:
+            nn.init.orthogonal_(param, gain=gain)
+    return layer
+
+
+def preproc_layer(input_size, output_size, is_sn=False):
+    layer = orthogonal_init(nn.Linear(input_size, output_size))
+    return spectral_norm(layer) if is_sn else layer
+
+
+# ---- dataset shims: same constructors as the reference's (they only carry tensors to the encoder) -----------------
+class AttributeDataset:
+    def __init__(self, attribute, adjacent, is_critic=False):
+        self.attribute, self.adjacent, self.is_critic = attribute, adjacent, is_critic
+
+    def __len__(self):
+        return len(self.attribute)
+
+
+class EmbeddingDataset:
+    def __init__(self, attribute, adjacent, is_critic=False, depth=1):
+        self.attribute, self.adjacent, self.is_critic, self.depth = attribute, adjacent, is_critic, depth
+
+    def __len__(self):
+        return len(self.attribute)
+
+    def update(self, embedding, adjacent):
+        del self.attribute[0]
+        self.attribute.append(embedding)
+        self.adjacent = adjacent
+
+
+class EmbeddingDataset2(EmbeddingDataset):
+    def __len__(self):
+        return self.depth
+
+
+def _dataset_of(loader):
+    return getattr(loader, "dataset", loader)
+
+
+class DHGN(nn.Module):
+    """Encoder parameters (reference names).  `encode` is the fused forward used by both networks."""
+
+    def __init__(self, input_dim, embedding_dim, is_sn, algo_config, device):
+        super().__init__()
+        if algo_config.vertex_level_aggregator != "mean" or algo_config.fcra_aggregator != "mean":
+            # the reference's 'pool' / 'att' branches cannot run (Parameter(required_grad=...), masked_fill(mask, value=...))
+            raise NotImplementedError("only the 'mean' aggregators are functional in the reference")
+        self.ReLU = nn.ReLU()
+        self.MSG_layers = nn.ModuleList()
+        self.AGG_layers = nn.ModuleDict()
+        self.FCRA_layers = nn.ModuleList()
+        self.alpha = nn.ModuleDict()
+        self.algo_config, self.device = algo_config, device
+        self.input_dim, self.embedding_dim, self.depth = input_dim, embedding_dim, int(algo_config.depth)
+        mk = (lambda a, b: preproc_layer(a, b)) if is_sn else (lambda a, b: nn.Linear(a, b))
+        self.semantic_layer = mk(3 * embedding_dim + input_dim, embedding_dim)
+        for r in range(algo_config.num_relation):
+            self.MSG_layers.append(mk(2 * input_dim if r == 0 else input_dim, embedding_dim))
+        for _ in range(self.depth):
+            self.FCRA_layers.append(mk(2 * embedding_dim, embedding_dim))
+        self.AGG_layers["AGG_vertex_0"] = mk(embedding_dim, embedding_dim)
+        for k in range(self.depth):
+            self.AGG_layers[f"AGG_fcra_{k}"] = mk(embedding_dim, embedding_dim)
+
+    def encode(self, graph, all_ones, hist):
+        """graph: ops.GraphBatch of S samples; hist: list over k of (tensor, sample_stride, agent_stride) or contiguous
+        [S,N,E] tensors, k=0 the most recent.  Returns the FCRA output [S,N,E] (what the reference calls `embedding`)."""
+        S, N, E = graph.S, graph.N, self.embedding_dim
+        m = self.MSG_layers
+        agg = ops.message_agg(graph, all_ones, m[0].weight, m[0].bias, m[1].weight, m[1].bias, m[2].weight, m[2].bias)
+        av = self.AGG_layers["AGG_vertex_0"]
+        emb3 = torch.relu(torch.addmm(av.bias, agg.view(S * N * 3, E), av.weight.t())).view(S * N, 3 * E)
+        h = torch.addmm(self.semantic_layer.bias, torch.cat([graph.p.view(S * N, 4), emb3], dim=1),
+                        self.semantic_layer.weight.t())
+        for k in range(self.depth):
+            hk = hist[k]
+            if isinstance(hk, tuple):
+                nb = ops.fcra_agg(hk[0], graph.p_adj_bits, all_ones, S, N, E, hk[1], hk[2])
+            else:
+                nb = ops.fcra_agg(hk, graph.p_adj_bits, all_ones, S, N, E)
+            af, ff = self.AGG_layers[f"AGG_fcra_{k}"], self.FCRA_layers[k]
+            mk = torch.relu(torch.addmm(af.bias, nb.view(S * N, E), af.weight.t()))
+            h = torch.relu(torch.addmm(ff.bias, torch.cat([mk, h], dim=1), ff.weight.t()))
+        return h.view(S, N, E)
+
+    # reference signature: forward(attributes: DataLoader, historical_embeddings: DataLoader)
+    def forward(self, attributes, historical_embeddings):
+        graph, all_ones, lead = _graph_from_datasets(_dataset_of(attributes))
+        hd = _dataset_of(historical_embeddings)
+        hist = _history_from_dataset(hd, graph, lead)
+        out = self.encode(graph, all_ones, hist)
+        return out.view(*lead, graph.N, self.embedding_dim).unsqueeze(0)   # DataLoader(batch_size=1) adds a leading 1
+
+
+def _graph_from_datasets(ds):
+    """AttributeDataset(attribute=[p,e,o], adjacent=[p_adj,e_adj,o_adj]) -> GraphBatch (dense fp32 0/1 -> packed bits)."""
+    p, e, o = ds.attribute
+    p_adj, e_adj, o_adj = ds.adjacent
+    lead = tuple(p.shape[:-2])
+    N, O = p.shape[-2], o.shape[-2]
+    S = int(np.prod(lead)) if lead else 1
+    dev = p.device
+    pf = p.reshape(S, N, 4).float().contiguous()
+    ef = e.reshape(S, 4).float().contiguous()
+    oxy = o.reshape(S, O, 4)[..., :2].float().contiguous()
+    graph = ops.GraphBatch(pf, ef, oxy, torch.arange(S, dtype=torch.int32, device=dev),
+                           torch.full((S,), O, dtype=torch.int32, device=dev),
+                           ops.pack_bits(p_adj.reshape(S, N, N)), (e_adj.reshape(S, N) != 0).to(torch.uint8).contiguous(),
+                           ops.pack_bits(o_adj.reshape(S, N, O)))
+    return graph, bool(ds.is_critic), lead
+
+
+def _history_from_dataset(hd, graph, lead):
+    D = hd.depth
+    S, N = graph.S, graph.N
+    if isinstance(hd.attribute, (list, tuple)):          # rollout: list of [N,E], newest last (EmbeddingDataset)
+        return [hd.attribute[D - 1 - k].reshape(S, N, -1).float().contiguous() for k in range(D)]
+    T = lead[-1]                                           # training: [mb, T+D, N, E] (EmbeddingDataset2)
+    return [hd.attribute[:, D - 1 - k: D - 1 - k + T].reshape(S, N, -1).float().contiguous() for k in range(D)]
+
+
+class _SharedNet(nn.Module):
+    def _gru_weights(self):
+        g = self.GRU
+        return [(getattr(g, f"weight_ih_l{l}"), getattr(g, f"weight_hh_l{l}"), getattr(g, f"bias_ih_l{l}"),
+                 getattr(g, f"bias_hh_l{l}")) for l in range(self.num_layers)]
+
+    def features(self, emb_TRE, hidden_state):
+        """emb [T,R,E], hidden [L,R,E] -> (GRU outputs [T,R,E], new hidden [L,R,E])."""
+        return ops.gru_forward(emb_TRE, hidden_state, self._gru_weights(), self.num_layers)
+
+    def get_weights(self):
+        return {k: v.cpu() for k, v in self.state_dict().items()}
+
+    def set_weights(self, weights):
+        self.load_state_dict(weights)
+
+    def get_gradients(self):
+        return [None if p.grad is None else p.grad.data.cpu().numpy() for p in self.parameters()]
+
+    def set_gradients(self, gradients, device):
+        for g, p in zip(gradients, self.parameters()):
+            if g is not None:
+                g = torch.as_tensor(g).to(device)
+                if p.grad is not None and p.grad.shape == g.shape:
+                    p.grad.copy_(g)            # keeps the flat-arena view alive
+                else:
+                    p.grad = g
+
+
+class SharedActor(_SharedNet):
+    def __init__(self, shared_net, rnn_input_dim, action_dim, num_layers, rnn_hidden_dim, is_sn=False):
+        super().__init__()
+        self.shared_net = shared_net
+        self.num_layers, self.rnn_input_dim, self.rnn_hidden_dim = num_layers, rnn_input_dim, rnn_hidden_dim
+        self.GRU = nn.GRU(rnn_input_dim, rnn_hidden_dim, num_layers)
+        self.Mean = preproc_layer(rnn_hidden_dim, action_dim) if is_sn else nn.Linear(rnn_hidden_dim, action_dim)
+
+    def forward(self, attributes, historical_embeddings, hidden_state, mode):
+        embedding = self.shared_net(attributes, historical_embeddings)          # [1, (mb, T,) N, E]
+        if mode == 0:
+            feat, hidden_state = self.features(embedding, hidden_state)
+            feature = feat.squeeze(0)
+        else:
+            emb = embedding.squeeze(0)
+            mb, T, N, E = emb.shape
+            feat, hidden_state = self.features(emb.permute(1, 0, 2, 3).reshape(T, mb * N, E), hidden_state)
+            feature = feat.reshape(T, mb, N, E).permute(1, 0, 2, 3)
+        prob = torch.softmax(torch.nn.functional.linear(feature, self.Mean.weight, self.Mean.bias), dim=-1)
+        return prob, hidden_state, embedding
+
+    def choose_action(self, attributes, historical_embeddings, hidden_state, deterministic=True, seed=0, t=0):
+        embedding = self.shared_net(attributes, historical_embeddings)
+        feat, hidden_state = self.features(embedding, hidden_state)
+        a, _, logp, _ = ops.act_head(feat[0], None, self.Mean.weight, self.Mean.bias, None, None, seed, t, deterministic)
+        if deterministic:
+            return a.long(), hidden_state, embedding
+        return a.long(), logp, hidden_state, embedding
+
+    def get_logprob_and_entropy(self, attributes, historical_embeddings, hidden_state, action):
+        prob, _, _ = self.forward(attributes, historical_embeddings, hidden_state, mode=1)
+        dist = torch.distributions.Categorical(prob)
+        return dist.log_prob(action), dist.entropy()
+
+
+class SharedCritic(_SharedNet):
+    def __init__(self, shared_net, rnn_input_dim, value_dim, num_layers, rnn_hidden_dim, is_sn=False):
+        super().__init__()
+        self.shared_net = shared_net
+        self.num_layers, self.rnn_input_dim, self.rnn_hidden_dim = num_layers, rnn_input_dim, rnn_hidden_dim
+        self.is_sn = is_sn
+        self.GRU = nn.GRU(rnn_input_dim, rnn_hidden_dim, num_layers)
+        self.Mean = preproc_layer(rnn_hidden_dim, value_dim, is_sn=is_sn)
+
+    def head_weight(self, update_buffers=True):
+        """Effective [1,E] weight.  With spectral norm the power iteration runs on every forward, rollout included
+        (the reference never calls .eval()), and updates weight_u / weight_v in place."""
+        if not self.is_sn:
+            return self.Mean.weight, None
+        W, u = self.Mean.weight_orig, self.Mean.weight_u
+        sigma, u2, v = ops.spectral_sigma(W, u)
+        if update_buffers:
+            with torch.no_grad():
+                self.Mean.weight_u.copy_(u2)
+                self.Mean.weight_v.copy_(v)
+        return W / sigma, u
+
+    def forward(self, attributes, historical_embeddings, hidden_state, mode):
+        embedding = self.shared_net(attributes, historical_embeddings)
+        w_eff, _ = self.head_weight()
+        if mode == 0:
+            feat, hidden_state = self.features(embedding, hidden_state)
+            val = torch.nn.functional.linear(feat.squeeze(0), w_eff, self.Mean.bias)
+            return val, hidden_state, embedding
+        emb = embedding.squeeze(0)
+        mb, T, N, E = emb.shape
+        feat, _ = self.features(emb.permute(1, 0, 2, 3).reshape(T, mb * N, E), hidden_state)
+        feature = feat.reshape(T, mb, N, E).permute(1, 0, 2, 3)
+        return torch.nn.functional.linear(feature, w_eff, self.Mean.bias)
+
+
+class _FlatAdam:
+    """torch.optim.Adam(lr, eps=1e-5) over one flat parameter/gradient arena, stepped by our fused kernel.
+    Exposes the slice of the optimizer API the reference touches: zero_grad(), step(), param_groups[i]['lr']."""
+
+    def __init__(self, params, lr, eps=1e-5, betas=(0.9, 0.999)):
+        self.params = params
+        self.param_groups = [dict(lr=lr, eps=eps, betas=betas, params=params)]
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self.step_count = 0
+        off = 0
+        self._views = []
+        for p in params:
+            k = p.numel()
+            self.flat_param[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + k].view_as(p.data)
+            p.grad = self.flat_grad[off:off + k].view_as(p.data)
+            self._views.append((off, k))
+            off += k
+
+    def _sync_grads(self):
+        for p, (off, k) in zip(self.params, self._views):
+            view = self.flat_grad[off:off + k]
+            if p.grad is None:
+                view.zero_()
+                p.grad = view.view_as(p.data)
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad.reshape(-1))
+                p.grad = view.view_as(p.data)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+        self._sync_grads()
+
+    def step(self):
+        self._sync_grads()
+        self.step_count += 1
+        g = self.param_groups[0]
+        ops.adam_step_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count,
+                       betas=g["betas"], eps=g["eps"])
+
+
+class TrainBatch:
+    """Training data in the engine's canonical form: time-major, bit-packed adjacency.  Built from a reference-layout
+    dict (`from_reference`, [B,T,...] dense fp32 as in DHGN/replay_buffer.py:28-40) or directly from a rollout."""
+
+    KEYS = ("p", "e", "p_adj_bits", "e_adj", "o_adj_bits", "hist_a", "hist_c", "v", "a", "logp", "r", "active")
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+        self.T, self.B, self.N = self.p.shape[:3]
+
+    @classmethod
+    def from_reference(cls, d, depth):
+        tm = lambda x: x.transpose(0, 1).contiguous()
+        B = d["p_state"].shape[0]
+        O = d["o_state"].shape[2]
+        dev = d["p_state"].device
+        return cls(p=tm(d["p_state"]).float(), e=tm(d["e_state"])[:, :, 0].contiguous().float(),
+                   oxy=d["o_state"][:, 0, :, :2].contiguous().float(),
+                   o_count_train=torch.full((B,), O, dtype=torch.int32, device=dev),
+                   p_adj_bits=ops.pack_bits(tm(d["p_adj"])), e_adj=(tm(d["e_adj"])[..., 0] != 0).to(torch.uint8).contiguous(),
+                   o_adj_bits=ops.pack_bits(tm(d["o_adj"])), hist_a=tm(d["actor_historical_embedding"]).float(),
+                   hist_c=tm(d["critic_historical_embedding"]).float(), v=tm(d["v_n"]).float(), a=tm(d["a_n"]).float(),
+                   logp=tm(d["a_logprob_n"]).float(), r=tm(d["r"]).float(), active=tm(d["active"]).float(), depth=depth)
+
+    def minibatch(self, lo, hi):
+        """Envs [lo, hi): contiguous copies of the time-major slabs (the reference's sequential `batch[key][index]`)."""
+        s = lambda x: x[:, lo:hi].contiguous()
+        mb = TrainBatch(p=s(self.p), e=s(self.e), oxy=self.oxy[lo:hi].contiguous(),
+                        o_count_train=self.o_count_train[lo:hi].contiguous(), p_adj_bits=s(self.p_adj_bits),
+                        e_adj=s(self.e_adj), o_adj_bits=s(self.o_adj_bits), hist_a=s(self.hist_a), hist_c=s(self.hist_c),
+                        v=s(self.v), a=s(self.a), logp=s(self.logp), r=s(self.r), active=s(self.active), depth=self.depth)
+        return mb
+
+    def graph(self):
+        T, B, N = self.T, self.B, self.N
+        o_index = torch.arange(B, dtype=torch.int32, device=self.p.device).repeat(T)
+        return ops.GraphBatch(self.p.view(T * B, N, 4), self.e.view(T * B, 4), self.oxy, o_index, self.o_count_train,
+                              self.p_adj_bits.view(T * B, N, -1), self.e_adj.view(T * B, N),
+                              self.o_adj_bits.view(T * B, N, -1))
+
+    def history(self, which):
+        """EmbeddingDataset2 (:95-113): k-th history = slabs [D-1-k, D-1-k+T) of the [T+D,B,N,E] arena — addressed in
+        place through strides, no copy."""
+        h = self.hist_a if which == "actor" else self.hist_c
+        D, T, B, N = self.depth, self.T, self.B, self.N
+        E = h.shape[-1]
+        return [(h[D - 1 - k:], N * E, E) for k in range(D)]
+
+
+class MAPPO:
+    def __init__(self, cfg, batch_size, mini_batch_size, agent_type):
+        a = cfg.algo
+        self.batch_size, self.mini_batch_size = batch_size, mini_batch_size
+        self.max_train_steps, self.lr, self.gamma, self.lamda = a.max_train_steps, a.lr, a.gamma, a.lamda
+        self.epsilon, self.K_epochs, self.entropy_coef = a.epsilon, a.epochs, a.entropy_coef
+        self.use_grad_clip, self.use_lr_decay = a.use_grad_clip, a.use_lr_decay
+        self.use_adv_norm, self.use_value_clip = a.use_adv_norm, a.use_value_clip
+        self.action_dim, self.input_dim = cfg.env.action_dim, cfg.env.state_dim
+        self.num_layers, self.embedding_dim = a.num_layers, a.embedding_dim
+        self.rnn_input_dim, self.rnn_hidden_dim = a.embedding_dim, a.rnn_hidden_dim
+        self.sn = a.use_spectral_norm
+        key = "learner_device" if "Learner" in agent_type else ("worker_device" if "Worker" in agent_type else "evaluator_device")
+        self.device = torch.device(getattr(a, key))
+        if self.device.type != "cuda":
+            raise _lib.MarlError(f"algo.{key}={self.device}: this engine runs on CUDA only (no CPU fallback)")
+        if not self.use_value_clip:
+            raise NotImplementedError("use_value_clip=False is not wired into the fused head kernel")
+        if a.use_reward_norm:
+            self.reward_norm = Normalization(shape=cfg.env.num_defender)
+        encoder = DHGN(self.input_dim, self.embedding_dim, self.sn, a, self.device)
+        self.depth = a.depth
+        self.actor = SharedActor(encoder, self.rnn_input_dim, self.action_dim, self.num_layers, self.rnn_hidden_dim, self.sn)
+        self.critic = SharedCritic(encoder, self.rnn_input_dim, 1, self.num_layers, self.rnn_hidden_dim, self.sn)
+        self.actor, self.critic = self.actor.to(self.device), self.critic.to(self.device)
+        self.ac_parameters = (list(self.actor.shared_net.parameters()) + list(self.actor.GRU.parameters()) +
+                              list(self.critic.GRU.parameters()) + list(self.critic.Mean.parameters()) +
+                              list(self.actor.Mean.parameters()))
+        self.ac_optimizer = _FlatAdam(self.ac_parameters, lr=self.lr, eps=1e-5)
+        self.minibuffer, self.total_step, self.cfg = None, 0, cfg
+
+    # ------------------------------------------------------------------------------------------------ training
+    def _forward_losses(self, mb, adv, v_target):
+        T, B, N, E = mb.T, mb.B, mb.N, self.embedding_dim
+        graph = mb.graph()
+        enc = self.actor.shared_net
+        h0 = torch.zeros(self.num_layers, B * N, E, dtype=torch.float32, device=self.device)
+        emb_a = enc.encode(graph, False, mb.history("actor"))
+        feat_a, _ = self.actor.features(emb_a.view(T, B * N, E), h0)
+        emb_c = enc.encode(graph, True, mb.history("critic"))
+        feat_c, _ = self.critic.features(emb_c.view(T, B * N, E), h0)
+        cm = self.critic.Mean
+        R = T * B * N
+        flat = lambda x: x.reshape(R)
+        la, lc, logp, ent, val, u2, v2 = ops.ppo_head(
+            feat_a.reshape(R, E), feat_c.reshape(R, E), self.actor.Mean.weight, self.actor.Mean.bias,
+            cm.weight_orig if self.sn else cm.weight, cm.bias, cm.weight_u if self.sn else torch.ones(1, device=self.device),
+            flat(mb.a), flat(mb.logp), flat(adv), flat(mb.v[:-1]), flat(v_target), flat(mb.active), self.epsilon,
+            self.entropy_coef)
+        if self.sn:
+            with torch.no_grad():
+                cm.weight_u.copy_(u2)
+                cm.weight_v.copy_(v2)
+        return la, lc, logp.view(T, B, N), ent.view(T, B, N), val.view(T, B, N)
+
+    def gae(self, tb):
+        """GAE + advantage normalisation on a time-major TrainBatch (kernel 3b)."""
+        L = _lib.lib()
+        import ctypes
+        T, B, N = tb.T, tb.B, tb.N
+        adv, vt = torch.empty_like(tb.r), torch.empty_like(tb.r)
+        ws = torch.zeros(int(L.marl_gae_workspace_bytes(B, T, N)), dtype=torch.uint8, device=tb.r.device)
+        _lib.check(L.marl_gae(B, T, N, _lib.ptr(tb.r), _lib.ptr(tb.v), _lib.ptr(tb.active), 1, ctypes.c_float(self.gamma),
+                              ctypes.c_float(self.gamma * self.lamda), 1 if self.use_adv_norm else 0, _lib.ptr(adv),
+                              _lib.ptr(vt), _lib.ptr(ws), _lib.stream_ptr()), "marl_gae")
+        return adv, vt
+
+    def train(self, replay_buffer, total_steps, return_numpy=True, trace=None):
+        """MAPPO.train (:638-723): GAE, then for each sequential minibatch forward / PPO losses / backward with gradients
+        accumulating and the global-norm clip applied to the running accumulation; no optimizer step here."""
+        data = replay_buffer.get_training_data(self.device) if hasattr(replay_buffer, "get_training_data") else replay_buffer
+        tb = data if isinstance(data, TrainBatch) else TrainBatch.from_reference(data, self.depth)
+        adv, v_target = self.gae(tb)
+        if trace is not None:
+            trace["adv"], trace["v_target"] = adv, v_target
+        self.ac_optimizer.zero_grad()
+        B = tb.B
+        bs = self.batch_size or B
+        mbs = self.mini_batch_size or bs
+        obj_c = obj_a = 0.0
+        n_updates = 0
+        with torch.enable_grad():
+            for lo in range(0, bs, mbs):
+                hi = min(lo + mbs, bs)
+                mb = tb.minibatch(lo, hi)
+                la, lc, logp, ent, val = self._forward_losses(mb, adv[:, lo:hi].contiguous(), v_target[:, lo:hi].contiguous())
+                (la + lc).backward()
+                if self.use_grad_clip:
+                    ops.clip_grad_norm_(self.ac_optimizer.flat_grad, 5.0)
+                if trace is not None:
+                    trace.setdefault("mb", []).append(dict(logp=logp.detach(), ent=ent.detach(), val=val.detach(),
+                                                           actor_loss=float(la), critic_loss=float(lc)))
+                obj_c += float(lc)
+                obj_a += float(la)
+                n_updates += 1
+        if self.use_lr_decay:
+            self.lr_decay(total_steps)
+        if return_numpy:
+            return obj_c / n_updates, obj_a / n_updates, self.actor.get_gradients(), self.critic.get_gradients()
+        return obj_c / n_updates, obj_a / n_updates, None, None
+
+    def lr_decay(self, total_steps):
+        lr_now = self.lr * (1 - total_steps / self.max_train_steps)
+        for p in self.ac_optimizer.param_groups:
+            p["lr"] = lr_now
+        self.total_step = total_steps
+
+    def save_model(self, cwd):
+        torch.save(self.actor.state_dict(), cwd + "actor.pth")
+        torch.save(self.critic.state_dict(), cwd + "critic.pth")
+
+    # ------------------------------------------------------------------------------------------------ rollout
+    @torch.no_grad()
+    def rollout_batched(self, engine, arena, T=None, seed=0, deterministic=False, groups=1):
+        """MAPPO.run_episode (:742-827) for all B envs of a BatchedPursuitEnv at once, entirely on the GPU.
+        Per step: observe kernel -> fused encoder (actor, then critic with all-ones adjacency) -> GRU cell -> heads ->
+        closed-loop env kernel (evader move + pursuer step + reward-norm + store).  Fills `arena` plus the history /
+        value / log-prob slabs and returns a TrainBatch ready for `train`."""
+        T = T or arena.T
+        B, N, E, D, L = engine.B, engine.N, self.embedding_dim, self.depth, self.num_layers
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        hist_a, hist_c = torch.zeros(T + D, B, N, E, **f32), torch.zeros(T + D, B, N, E, **f32)
+        v = torch.zeros(T + 1, B, N, **f32)
+        logp = torch.zeros(T, B, N, **f32)
+        act = torch.zeros(T, B, N, dtype=torch.int32, device=dev)
+        ha, hc = torch.zeros(L, B * N, E, **f32), torch.zeros(L, B * N, E, **f32)
+        oxy = engine.boundary_xy.to(torch.float32).contiguous()                 # [M,O,2]
+        o_count = torch.clamp(engine.boundary_count, max=engine.O).contiguous()  # rollout: the O_b real cells
+        enc = self.actor.shared_net
+        zeros_hist = torch.zeros(B, N, E, **f32)
+        w_eff = None
+
+        def history(t):
+            # one aliased list for both nets (:750-752): newest first = C(t-1), A(t-1), C(t-2), A(t-2), ...
+            out = []
+            for k in range(D):
+                back = k // 2 + 1
+                src = hist_c if k % 2 == 0 else hist_a
+                out.append(src[t - back + D] if t - back >= 0 else zeros_hist)
+            return out
+
+        def critic_step(t, graph):
+            nonlocal hc, w_eff
+            emb_c = enc.encode(graph, True, history(t))
+            feat_c, hc = self.critic.features(emb_c.view(1, B * N, E), hc)
+            w, _ = self.critic.head_weight()
+            w_eff = w.reshape(E).contiguous()
+            return emb_c, feat_c[0]
+
+        for t in range(T):
+            engine.observe()
+            graph = ops.GraphBatch(engine.p_state.to(torch.float32), engine.e_state.to(torch.float32), oxy, engine.map_id,
+                                   o_count, engine.p_adj_bits, engine.e_adj, engine.o_adj_bits)
+            emb_a = enc.encode(graph, False, history(t))
+            feat_a, ha = self.actor.features(emb_a.view(1, B * N, E), ha)
+            emb_c, feat_c = critic_step(t, graph)
+            a_i, _, lp, val = ops.act_head(feat_a[0], feat_c, self.actor.Mean.weight, self.actor.Mean.bias, w_eff,
+                                           self.critic.Mean.bias, seed, t, deterministic)
+            hist_a[t + D], hist_c[t + D] = emb_a, emb_c
+            v[t], logp[t], act[t] = val.view(B, N), lp.view(B, N), a_i.view(B, N)
+            engine.rollout_closed(arena, 1, t0=t, action_tape=act[t:t + 1], env_t0=t, groups=groups)
+        # bootstrap value of the final state (:806-825): only the critic's dataset is updated once more
+        engine.observe()
+        graph = ops.GraphBatch(engine.p_state.to(torch.float32), engine.e_state.to(torch.float32), oxy, engine.map_id,
+                               o_count, engine.p_adj_bits, engine.e_adj, engine.o_adj_bits)
+        hist_final = [hist_c[T - 1 + D]] + history(T - 1)[:D - 1]
+        emb_c = enc.encode(graph, True, hist_final)
+        feat_c, hc = self.critic.features(emb_c.view(1, B * N, E), hc)
+        w, _ = self.critic.head_weight()
+        v[T] = torch.nn.functional.linear(feat_c[0], w, self.critic.Mean.bias).view(B, N)
+        oxy_env = oxy[engine.map_id.long()].contiguous()
+        return TrainBatch(p=arena.p_state_f32[:T], e=arena.e_state_f32[:T, :, 0].contiguous(), oxy=oxy_env,
+                          o_count_train=torch.full((B,), engine.O, dtype=torch.int32, device=dev),
+                          p_adj_bits=arena.p_adj_bits[:T], e_adj=arena.e_adj[:T], o_adj_bits=arena.o_adj_bits[:T],
+                          hist_a=hist_a, hist_c=hist_c, v=v, a=arena.a_n[:T], logp=logp, r=arena.r[:T],
+                          active=arena.active[:T], depth=D)
+
+    def explore_env(self, env, num_episode):
+        """Reference signature (:731-740) for the single-env facade `Pursuit_Env`: returns
+        (mean episode reward, ReplayBuffer in the reference layout, steps)."""
+        from .pursuit_env import RolloutArena
+        self.minibuffer = ReplayBuffer(cfg=self.cfg, device=self.device)
+        self.minibuffer.reset_buffer()
+        total_r, steps = 0.0, 0
+        for k in range(num_episode):
+            env.reset()
+            eng = env.engine
+            self.reward_norm.to_engine(eng)
+            arena = RolloutArena(eng.params, 1, env.max_steps, eng.device)
+            env.begin_batched_episode()
+            tb = self.rollout_batched(eng, arena, env.max_steps, seed=int(torch.randint(0, 2 ** 31, (1,)).item()))
+            self.reward_norm.from_engine(eng)
+            env.end_batched_episode()
+            total_r += float(arena.raw_reward.sum().item())
+            steps += env.max_steps
+            self.minibuffer.store_episode(k, arena, tb)
+        return total_r / num_episode, self.minibuffer, steps
+
+    def run_episode(self, env, num_episode=0):
+        r, _, steps = self.explore_env(env, 1)
+        return r, steps

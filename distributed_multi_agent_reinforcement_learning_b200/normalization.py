@@ -1,0 +1,80 @@
+"""Running mean/std normalisation — mirror of the reference `DHGN/normalization.py` (RunningMeanStd, Normalization,
+RewardScaling) with the statistics updated by the Welford kernel (csrc/stats_kernels.cu, marl_welford_update).
+
+Semantics kept (DHGN/normalization.py:11-22): on the first sample `mean = x` and `std = x` (so the first output is 0),
+afterwards the population std `sqrt(S/n)`; the estimate is never reset across episodes (one per worker)."""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class RunningMeanStd:
+    def __init__(self, shape, device="cuda:0"):
+        self.shape = int(shape)
+        self.device = torch.device(device)
+        self._n = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._mean = torch.zeros(1, self.shape, dtype=torch.float64, device=self.device)
+        self._S = torch.zeros_like(self._mean)
+        self._std = torch.zeros_like(self._mean)
+        self._out = torch.zeros(1, self.shape, dtype=torch.float32, device=self.device)
+
+    n = property(lambda s: int(s._n.item()))
+    mean = property(lambda s: s._mean[0].cpu().numpy())
+    S = property(lambda s: s._S[0].cpu().numpy())
+    std = property(lambda s: s._std[0].cpu().numpy())
+
+    def update(self, x):
+        self._run(x, True)
+
+    def _run(self, x, update):
+        x = torch.as_tensor(np.asarray(x).astype(np.int32).reshape(1, self.shape), device=self.device)
+        if not np.array_equal(np.asarray(x.cpu()), np.asarray(x.cpu()).astype(np.int64)):
+            raise _lib.MarlError("Normalization: rewards of this env are integers")
+        _lib.check(_lib.lib().marl_welford_update(1, self.shape, _lib.ptr(x), _lib.ptr(self._n), _lib.ptr(self._mean),
+                                                  _lib.ptr(self._S), _lib.ptr(self._std), _lib.ptr(self._out),
+                                                  1 if update else 0, _lib.stream_ptr()), "marl_welford_update")
+        return x
+
+
+class Normalization:
+    def __init__(self, shape, device="cuda:0"):
+        self.running_ms = RunningMeanStd(shape=shape, device=device)
+
+    def __call__(self, x, update=True):
+        """-> np.ndarray float64 [(x - mean) / (std + 1e-8)], like the reference."""
+        ms = self.running_ms
+        ms._run(x, update)
+        xs = np.asarray(x, dtype=np.float64)
+        return (xs - ms.mean) / (ms.std + 1e-8)
+
+    # the batched engine keeps one estimate per env; these move the single-env estimate in and out of a B=1 engine
+    def to_engine(self, eng):
+        ms = self.running_ms
+        eng.wf_n.copy_(ms._n)
+        eng.wf_mean.copy_(ms._mean)
+        eng.wf_S.copy_(ms._S)
+        eng.wf_std.copy_(ms._std)
+
+    def from_engine(self, eng):
+        ms = self.running_ms
+        ms._n.copy_(eng.wf_n)
+        ms._mean.copy_(eng.wf_mean)
+        ms._S.copy_(eng.wf_S)
+        ms._std.copy_(eng.wf_std)
+
+
+class RewardScaling:
+    """DHGN/normalization.py:38-52 (unused by the reference's training loop; kept for API completeness)."""
+
+    def __init__(self, shape, gamma, device="cuda:0"):
+        self.shape, self.gamma = shape, gamma
+        self.running_ms = RunningMeanStd(shape=shape, device=device)
+        self.R = np.zeros(self.shape)
+
+    def __call__(self, x):
+        raise NotImplementedError("RewardScaling feeds non-integer returns to the running estimate; the Welford kernel "
+                                  "of this engine is specialised to the env's integer rewards")
+
+    def reset(self):
+        self.R = np.zeros(self.shape)

@@ -1,0 +1,234 @@
+"""Autograd bindings of kernel family 5 (csrc/policy_kernels.cu) plus the small amount of torch glue around them.
+
+Only plain dense layers go through library GEMMs (torch.addmm / torch.mm -> cuBLAS); everything pairwise, sparse or
+pointwise is one of our kernels.  fp32 throughout (parity mode: TF32 is switched off for the GEMMs by the caller).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _L():
+    return _lib.lib()
+
+
+class GraphBatch:
+    """Inputs of the DHGN encoder for S samples (a sample = one env at one time step).
+
+    p [S,N,4] f32, e [S,4] f32, oxy [Bo,O,2] f32 (obstacle cells per map row), o_index [S] i32, o_count [Bo] i32,
+    p_adj_bits [S,N,NW] i32, e_adj [S,N] u8, o_adj_bits [S,N,OW] i32."""
+
+    def __init__(self, p, e, oxy, o_index, o_count, p_adj_bits, e_adj, o_adj_bits):
+        self.p, self.e, self.oxy, self.o_index, self.o_count = p, e, oxy, o_index, o_count
+        self.p_adj_bits, self.e_adj, self.o_adj_bits = p_adj_bits, e_adj, o_adj_bits
+        self.S, self.N = p.shape[0], p.shape[1]
+        self.O = oxy.shape[1]
+        for t in (p, e, oxy, o_index, o_count, p_adj_bits, e_adj, o_adj_bits):
+            assert t.is_contiguous() and t.is_cuda
+        assert p.dtype == torch.float32 and e.dtype == torch.float32 and oxy.dtype == torch.float32
+        assert o_index.dtype == torch.int32 and o_count.dtype == torch.int32 and e_adj.dtype == torch.uint8
+
+    def _args(self, E, all_ones):
+        P = _lib.ptr
+        return (self.S, self.N, self.O, E, P(self.p), P(self.e), P(self.oxy), P(self.o_index), P(self.o_count),
+                P(self.p_adj_bits), P(self.e_adj), P(self.o_adj_bits), 1 if all_ones else 0)
+
+
+def pack_bits(dense):
+    """float/bool 0-1 tensor [..., K] -> int32 words [..., ceil(K/32)] (bit k&31 of word k>>5)."""
+    K = dense.shape[-1]
+    KW = (K + 31) // 32
+    b = (dense != 0)
+    if KW * 32 != K:
+        b = torch.nn.functional.pad(b, (0, KW * 32 - K))
+    b = b.reshape(*dense.shape[:-1], KW, 32).to(torch.int64)
+    w = (b << torch.arange(32, device=dense.device, dtype=torch.int64)).sum(-1)
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
+    return w.to(torch.int32).contiguous()
+
+
+class _MessageAgg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, graph, all_ones, W0, b0, W1, b1, W2, b2):
+        E = W0.shape[0]
+        ws = [t.contiguous() for t in (W0, b0, W1, b1, W2, b2)]
+        agg = torch.empty(graph.S, graph.N, 3, E, dtype=torch.float32, device=W0.device)
+        _lib.check(_L().marl_dhgn_message_fwd(*graph._args(E, all_ones), *[_lib.ptr(t) for t in ws], _lib.ptr(agg),
+                                              _lib.stream_ptr()), "marl_dhgn_message_fwd")
+        ctx.graph, ctx.all_ones = graph, all_ones
+        ctx.save_for_backward(*ws)
+        return agg
+
+    @staticmethod
+    def backward(ctx, d_agg):
+        ws = ctx.saved_tensors
+        E = ws[0].shape[0]
+        grads = [torch.zeros_like(t) for t in ws]
+        _lib.check(_L().marl_dhgn_message_bwd(*ctx.graph._args(E, ctx.all_ones), *[_lib.ptr(t) for t in ws],
+                                              _lib.ptr(d_agg.contiguous()), *[_lib.ptr(g) for g in grads],
+                                              _lib.stream_ptr()), "marl_dhgn_message_bwd")
+        return (None, None, *grads)
+
+
+def message_agg(graph, all_ones, W0, b0, W1, b1, W2, b2):
+    """[S,N,3,E]: mean-aggregated ReLU messages of the three relations (input of AGG_vertex_0)."""
+    return _MessageAgg.apply(graph, all_ones, W0, b0, W1, b1, W2, b2)
+
+
+def fcra_agg(hist, p_adj_bits, all_ones, S, N, E, sample_stride=None, agent_stride=None):
+    """L1norm(adj) @ hist (no gradient: history embeddings are data).  hist: tensor whose element (s,j,:) lives at
+    data_ptr + (s*sample_stride + j*agent_stride)*4 bytes (defaults: contiguous [S,N,E])."""
+    out = torch.empty(S, N, E, dtype=torch.float32, device=hist.device)
+    ss = N * E if sample_stride is None else sample_stride
+    as_ = E if agent_stride is None else agent_stride
+    _lib.check(_L().marl_fcra_agg(S, N, E, hist.data_ptr(), ss, as_, _lib.ptr(p_adj_bits), 1 if all_ones else 0,
+                                  _lib.ptr(out), _lib.stream_ptr()), "marl_fcra_agg")
+    return out
+
+
+class _GRULayer(torch.autograd.Function):
+    """One nn.GRU layer over a whole sequence: the input projection is one GEMM over all steps, the recurrence is
+    one [R,E]x[E,3E] GEMM + one fused cell kernel per step."""
+
+    @staticmethod
+    def forward(ctx, x, h0, w_ih, w_hh, b_ih, b_hh):
+        T, R, E = x.shape
+        need = any(ctx.needs_input_grad)
+        x = x.contiguous()
+        gi_all = torch.addmm(b_ih, x.view(T * R, E), w_ih.t()).view(T, R, 3 * E)
+        out = torch.empty(T, R, E, dtype=x.dtype, device=x.device)
+        saves = torch.empty(4, T, R, E, dtype=x.dtype, device=x.device) if need else None
+        gh = torch.empty(R, 3 * E, dtype=x.dtype, device=x.device)
+        w_hh_t = w_hh.t()
+        h = h0.contiguous()
+        L, P, st = _L(), _lib.ptr, _lib.stream_ptr()
+        for t in range(T):
+            torch.addmm(b_hh, h, w_hh_t, out=gh)
+            sv = [saves[k, t].data_ptr() for k in range(4)] if need else [None] * 4
+            _lib.check(L.marl_gru_cell_fwd(R, E, gi_all[t].data_ptr(), P(gh), h.data_ptr(), out[t].data_ptr(), *sv, st),
+                       "marl_gru_cell_fwd")
+            h = out[t]
+        if need:
+            ctx.save_for_backward(x, h0, w_ih, w_hh, out, saves)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, h0, w_ih, w_hh, out, saves = ctx.saved_tensors
+        T, R, E = x.shape
+        d_out = d_out.contiguous()
+        dgi = torch.empty(T, R, 3 * E, dtype=x.dtype, device=x.device)
+        dgh = torch.empty(T, R, 3 * E, dtype=x.dtype, device=x.device)
+        dh = torch.zeros(R, E, dtype=x.dtype, device=x.device)
+        dh_tot = torch.empty_like(dh)
+        dh_prev = torch.empty_like(dh)
+        h0c = h0.contiguous()
+        L, st = _L(), _lib.stream_ptr()
+        for t in range(T - 1, -1, -1):
+            torch.add(d_out[t], dh, out=dh_tot)
+            hp = out[t - 1] if t > 0 else h0c
+            _lib.check(L.marl_gru_cell_bwd(R, E, dh_tot.data_ptr(), saves[0, t].data_ptr(), saves[1, t].data_ptr(),
+                                           saves[2, t].data_ptr(), saves[3, t].data_ptr(), hp.data_ptr(),
+                                           dgi[t].data_ptr(), dgh[t].data_ptr(), dh_prev.data_ptr(), st),
+                       "marl_gru_cell_bwd")
+            torch.addmm(dh_prev, dgh[t], w_hh, out=dh)          # dh_{t-1} = dh_t*z + dgh_t @ W_hh
+        dgi2, dgh2 = dgi.view(T * R, 3 * E), dgh.view(T * R, 3 * E)
+        h_prev_all = torch.cat([h0c.unsqueeze(0), out[:-1]], dim=0).view(T * R, E)
+        dx = torch.mm(dgi2, w_ih).view(T, R, E)
+        return dx, dh.clone(), torch.mm(dgi2.t(), x.view(T * R, E)), torch.mm(dgh2.t(), h_prev_all), dgi2.sum(0), dgh2.sum(0)
+
+
+def gru_forward(x, h0, weights, num_layers):
+    """weights: list per layer of (w_ih, w_hh, b_ih, b_hh); x [T,R,E]; h0 [L,R,E] -> (out [T,R,E], hT [L,R,E])."""
+    hs = []
+    for layer in range(num_layers):
+        x = _GRULayer.apply(x, h0[layer], *weights[layer])
+        hs.append(x[-1])
+    return x, torch.stack(hs)
+
+
+def spectral_sigma(W, u):
+    """One power iteration of torch.nn.utils.spectral_norm (exact for the [1,E] critic head).  Returns
+    (sigma, u_new, v_new); sigma is to be treated as u^T W v with u, v constants."""
+    with torch.no_grad():
+        v = torch.nn.functional.normalize(torch.mv(W.t(), u), dim=0, eps=1e-12)
+        u2 = torch.nn.functional.normalize(torch.mv(W, v), dim=0, eps=1e-12)
+        sigma = torch.dot(u2, torch.mv(W, v))
+    return sigma, u2, v
+
+
+class _PPOHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat_a, feat_c, Wa, ba, Wc_orig, bc, u, action, old_logp, adv, v_old, v_target, active, eps, ent_coef):
+        R, E = feat_a.shape
+        A = Wa.shape[0]
+        sigma, u2, v = spectral_sigma(Wc_orig, u)
+        w_eff = (Wc_orig / sigma).reshape(E).contiguous()
+        dev = feat_a.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        logp, ent, val = torch.empty(R, **f32), torch.empty(R, **f32), torch.empty(R, **f32)
+        dlogits, dvalue, sums = torch.empty(R, A, **f32), torch.empty(R, **f32), torch.zeros(3, **f32)
+        args = [t.contiguous() for t in (feat_a, feat_c, Wa, ba, w_eff, bc, action, old_logp, adv, v_old, v_target, active)]
+        _lib.check(_L().marl_ppo_head(R, E, A, *[_lib.ptr(t) for t in args], ctypes.c_float(eps), ctypes.c_float(ent_coef),
+                                      _lib.ptr(logp), _lib.ptr(ent), _lib.ptr(val), _lib.ptr(dlogits), _lib.ptr(dvalue),
+                                      _lib.ptr(sums), _lib.stream_ptr()), "marl_ppo_head")
+        ctx.save_for_backward(args[0], args[1], args[2], w_eff, dlogits, dvalue, sums, sigma, u2, v)
+        ctx.mark_non_differentiable(logp, ent, val, u2, v)
+        return sums[0] / sums[2], sums[1] / sums[2], logp, ent, val, u2, v
+
+    @staticmethod
+    def backward(ctx, g_actor, g_critic, *_unused):
+        feat_a, feat_c, Wa, w_eff, dlogits, dvalue, sums, sigma, u2, v = ctx.saved_tensors
+        dl = dlogits * (g_actor / sums[2])
+        dv = dvalue * (g_critic / sums[2])
+        d_feat_a = torch.mm(dl, Wa)
+        dWa = torch.mm(dl.t(), feat_a)
+        dba = dl.sum(0)
+        d_feat_c = dv.unsqueeze(1) * w_eff.unsqueeze(0)
+        dw_eff = torch.mv(feat_c.t(), dv)
+        dbc = dv.sum().reshape(1)
+        # W_eff = W / sigma, sigma = u^T W v  =>  dW = (dW_eff - <dW_eff, W_eff> u v^T) / sigma
+        dWc = (dw_eff.unsqueeze(0) - (dw_eff * w_eff).sum() * (u2.unsqueeze(1) * v.unsqueeze(0))) / sigma
+        return (d_feat_a, d_feat_c, dWa, dba, dWc, dbc) + (None,) * 9
+
+
+def ppo_head(feat_a, feat_c, Wa, ba, Wc_orig, bc, u, action, old_logp, adv, v_old, v_target, active, eps, ent_coef):
+    """-> (actor_loss, critic_loss, logp [R], entropy [R], value [R], u_new, v_new)."""
+    return _PPOHead.apply(feat_a, feat_c, Wa, ba, Wc_orig, bc, u, action, old_logp, adv, v_old, v_target, active,
+                          float(eps), float(ent_coef))
+
+
+def act_head(feat_a, feat_c, Wa, ba, w_eff, bc, seed, t, deterministic):
+    """Rollout heads: -> (action i32 [R], action f32 [R], logp [R], value [R] or None)."""
+    R, E = feat_a.shape
+    dev = feat_a.device
+    action = torch.empty(R, dtype=torch.int32, device=dev)
+    action_f = torch.empty(R, dtype=torch.float32, device=dev)
+    logp = torch.empty(R, dtype=torch.float32, device=dev)
+    value = torch.empty(R, dtype=torch.float32, device=dev) if feat_c is not None else None
+    _lib.check(_L().marl_act_head(R, E, Wa.shape[0], _lib.ptr(feat_a.contiguous()),
+                                  _lib.ptr(feat_c.contiguous()) if feat_c is not None else None, _lib.ptr(Wa.contiguous()),
+                                  _lib.ptr(ba.contiguous()), _lib.ptr(w_eff) if w_eff is not None else None,
+                                  _lib.ptr(bc) if bc is not None else None, ctypes.c_uint64(seed), int(t),
+                                  1 if deterministic else 0, _lib.ptr(action), _lib.ptr(action_f), _lib.ptr(logp),
+                                  _lib.ptr(value), _lib.stream_ptr()), "marl_act_head")
+    return action, action_f, logp, value
+
+
+def clip_grad_norm_(flat_grad, max_norm):
+    """In-place global-norm clip of a flat fp32 gradient arena; returns the pre-clip norm (0-dim tensor)."""
+    n = flat_grad.numel()
+    ws = torch.empty(int(_L().marl_clip_workspace_bytes(n)), dtype=torch.uint8, device=flat_grad.device)
+    total = torch.empty(1, dtype=torch.float32, device=flat_grad.device)
+    _lib.check(_L().marl_clip_grad_norm(n, _lib.ptr(flat_grad), ctypes.c_float(max_norm), _lib.ptr(ws), _lib.ptr(total),
+                                        _lib.stream_ptr()), "marl_clip_grad_norm")
+    return total[0]
+
+
+def adam_step_(flat_param, flat_grad, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-5):
+    _lib.check(_L().marl_adam_step(flat_param.numel(), _lib.ptr(flat_param), _lib.ptr(flat_grad), _lib.ptr(exp_avg),
+                                   _lib.ptr(exp_avg_sq), ctypes.c_float(lr), ctypes.c_float(betas[0]),
+                                   ctypes.c_float(betas[1]), ctypes.c_float(eps), int(step), _lib.stream_ptr()),
+               "marl_adam_step")

@@ -496,6 +496,31 @@ class Pursuit_Env:
             boundaries=tuple(self.map_config.map_size))
         self._pull()
 
+    # -- whole-episode hand-off to the batched rollout (MAPPO.explore_env) -----------------------------------------
+    def begin_batched_episode(self, tape_len=64):
+        """Pre-draws candidate targets from the global `random` stream for the device-side evader; the stream is put
+        back in `end_batched_episode` so that exactly as many draws are consumed as the reference would have made."""
+        import random
+        W, H = self.map_config.map_size
+        self._rng_state = random.getstate()
+        tape = [(random.randint(0, W - 1), random.randint(0, H - 1)) for _ in range(tape_len)]
+        random.setstate(self._rng_state)
+        self.engine.set_target_tape(np.asarray(tape, np.int32).reshape(1, tape_len, 2))
+
+    def end_batched_episode(self):
+        import random
+        eng = self.engine
+        status = int(eng.evader_status[0].item())
+        if status:
+            raise _lib.MarlError(f"evader status {status} (search overflow or target tape exhausted)")
+        W, H = self.map_config.map_size
+        for _ in range(int(eng.tape_pos[0].item())):          # replay the draws the episode actually consumed
+            random.randint(0, W - 1), random.randint(0, H - 1)
+        self.time_step = int(eng.time_step[0].item())
+        self.collision = bool(eng.collision[0].item())
+        self.target = [tuple(int(v) for v in eng.target[0].cpu().numpy())]
+        self._pull()
+
     def get_state(self, agent_type):
         if agent_type == "defender":
             return [[float(v) for v in row] for row in self._host_p]

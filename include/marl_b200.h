@@ -206,6 +206,56 @@ int marl_rollout_closed(const marl_env_params *p, int32_t B, int32_t B_stride, i
                         uint8_t *d_collision, int32_t *d_time_step,
                         const marl_rollout_records *rec, void *stream);
 
+/* ---- kernel family 5: DHGN actor/critic, the non-GEMM parts (fp32) -----------------------------------------
+ * The dense E-wide layers (AGG_vertex_0, semantic_layer, AGG_fcra_k, FCRA_layers.k, GRU weight matrices) are plain
+ * library GEMMs on the host side; these entry points fuse everything pairwise / sparse / pointwise around them so that
+ * no [.,N,N,8], [.,N,O,4] or dense 0/1 adjacency tensor is materialised.  E = embedding_dim in {32, 64, 128}.
+ *
+ * marl_dhgn_message_{fwd,bwd}: DHGN.message + L1-normalised mean aggregation of the three relations
+ * (DHGN/mappo_parallel.py:256-281,323-348) from bit-packed adjacency.  S samples x N agents;
+ * p f32 [S,N,4], e f32 [S,4], oxy f32 [Bo,O,2] + o_index i32 [S] + o_count i32 [Bo] (obstacle cells per map; the count
+ * is what "all ones" spans for the critic: O_b during rollout, O in training — :64-65);
+ * W0 [E,8], W1 [E,4], W2 [E,4] = MSG_layers.{0,1,2}.weight.  Out: agg f32 [S,N,3,E] (input of AGG_vertex_0).
+ * bwd accumulates (+=) the weight/bias gradients; inputs are data, so there is no input gradient. */
+int marl_dhgn_message_fwd(int32_t S, int32_t N, int32_t O, int32_t E, const float *d_p, const float *d_e,
+                          const float *d_oxy, const int32_t *d_o_index, const int32_t *d_o_count,
+                          const uint32_t *d_p_adj_bits, const uint8_t *d_e_adj, const uint32_t *d_o_adj_bits,
+                          int32_t all_ones, const float *d_W0, const float *d_b0, const float *d_W1, const float *d_b1,
+                          const float *d_W2, const float *d_b2, float *d_agg, void *stream);
+int marl_dhgn_message_bwd(int32_t S, int32_t N, int32_t O, int32_t E, const float *d_p, const float *d_e,
+                          const float *d_oxy, const int32_t *d_o_index, const int32_t *d_o_count,
+                          const uint32_t *d_p_adj_bits, const uint8_t *d_e_adj, const uint32_t *d_o_adj_bits,
+                          int32_t all_ones, const float *d_W0, const float *d_b0, const float *d_W1, const float *d_b1,
+                          const float *d_W2, const float *d_b2, const float *d_grad_agg, float *d_gW0, float *d_gb0,
+                          float *d_gW1, float *d_gb1, float *d_gW2, float *d_gb2, void *stream);
+/* L1norm(adj) @ hist of DHGN.fcra (:204-233): out[s,i,:] = mean over neighbours j of hist[s*sample_stride + j*agent_stride]. */
+int marl_fcra_agg(int32_t S, int32_t N, int32_t E, const float *d_hist, int64_t sample_stride, int64_t agent_stride,
+                  const uint32_t *d_p_adj_bits, int32_t all_ones, float *d_out, void *stream);
+/* torch.nn.GRU cell pointwise (gate order r,z,n) given gi = x W_ih^T + b_ih and gh = h W_hh^T + b_hh, both [R,3E]. */
+int marl_gru_cell_fwd(int64_t R, int32_t E, const float *d_gi, const float *d_gh, const float *d_h_prev,
+                      float *d_h_new, float *d_save_r, float *d_save_z, float *d_save_n, float *d_save_hn, void *stream);
+int marl_gru_cell_bwd(int64_t R, int32_t E, const float *d_dh_new, const float *d_save_r, const float *d_save_z,
+                      const float *d_save_n, const float *d_save_hn, const float *d_h_prev, float *d_dgi, float *d_dgh,
+                      float *d_dh_prev, void *stream);
+/* Actor softmax/Categorical + critic head + PPO-clip / clipped value losses, forward AND backward in one pass
+ * (:437,446-456,526,692-706).  Adds {sum actor_term*active, sum critic_term*active, sum active} to d_sums[3] and
+ * writes d(sum)/d logits [R,A], d(sum)/d value [R]; the caller divides by sum(active). */
+int marl_ppo_head(int64_t R, int32_t E, int32_t A, const float *d_feat_a, const float *d_feat_c, const float *d_Wa,
+                  const float *d_ba, const float *d_wc_eff, const float *d_bc, const float *d_action,
+                  const float *d_old_logp, const float *d_adv, const float *d_v_old, const float *d_v_target,
+                  const float *d_active, float eps, float ent_coef, float *d_logp, float *d_entropy, float *d_value,
+                  float *d_dlogits, float *d_dvalue, float *d_sums, void *stream);
+/* Rollout-time heads (:440-449, :513): softmax -> sample (counter RNG keyed by seed,row,t) or argmax -> log-prob; value. */
+int marl_act_head(int64_t R, int32_t E, int32_t A, const float *d_feat_a, const float *d_feat_c, const float *d_Wa,
+                  const float *d_ba, const float *d_wc_eff, const float *d_bc, uint64_t seed, int32_t t,
+                  int32_t deterministic, int32_t *d_action, float *d_action_f32, float *d_logp, float *d_value,
+                  void *stream);
+/* torch.nn.utils.clip_grad_norm_ (:710-711) and torch.optim.Adam.step (runner.py:72-78) on flat fp32 arenas. */
+int64_t marl_clip_workspace_bytes(int64_t n);
+int marl_clip_grad_norm(int64_t n, float *d_grad, float max_norm, void *d_workspace, float *d_total_norm, void *stream);
+int marl_adam_step(int64_t n, float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, float lr,
+                   float beta1, float beta2, float eps, int64_t step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
