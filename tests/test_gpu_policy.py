@@ -236,6 +236,7 @@ def test_gru_layer_forward_backward(E, T, R):
     torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
     # and against torch.nn.GRU itself (the module the reference uses)
     gru = torch.nn.GRU(E, E, 1).cuda()
+    torch.backends.cudnn.allow_tf32 = False               # cuDNN's RNN path would otherwise round the GEMMs to TF32
     with torch.no_grad():
         gru.weight_ih_l0.copy_(w["G.weight_ih_l0"]); gru.weight_hh_l0.copy_(w["G.weight_hh_l0"])
         gru.bias_ih_l0.copy_(w["G.bias_ih_l0"]); gru.bias_hh_l0.copy_(w["G.bias_hh_l0"])
@@ -334,3 +335,94 @@ def test_clip_and_adam_match_torch():
     before = small.clone()
     ops.clip_grad_norm_(small, 5.0)                       # below the threshold: untouched
     assert torch.equal(small, before)
+
+
+def test_batched_rollout_then_train_end_to_end():
+    """run_episode for a batch of envs on the GPU (observe -> encoder -> GRU -> heads -> env kernels), checked for
+    self-consistency against a teacher-forced replay of what it stored, then fed to train()."""
+    from distributed_multi_agent_reinforcement_learning_b200 import policy_ops as ops
+    from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
+    from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv, RolloutArena
+    import bench
+    B, N, M, T, E, D = 12, 4, 3, 14, 32, 3
+    cfg = _cfg(D, N, T, E)
+    torch.manual_seed(0)
+    m = MAPPO(cfg, B, 5, "Learner")
+    wl = bench.host_workload(cfg, B, M, seed=3)
+    env = BatchedPursuitEnv(cfg, B, num_maps=M)
+    env.set_maps(wl["grids"], wl["inflated"])
+    env.set_state(wl["p_state"], wl["e_state"], wl["target"], wl["map_id"], time_step=0)
+    env.set_target_tape(wl["tape"])
+    env.start_episode()
+    arena = RolloutArena(env.params, B, T, env.device)
+    tb = m.rollout_batched(env, arena, T, seed=11)
+    torch.cuda.synchronize()
+    assert int(env.evader_status.max()) == 0 and (env.time_step == T).all()
+    assert tb.p.shape == (T, B, N, 4) and tb.hist_a.shape == (T + D, B, N, E) and tb.v.shape == (T + 1, B, N)
+    assert torch.equal(tb.a, arena.a_n) and (tb.a >= 0).all() and (tb.a <= 8).all()
+    assert (tb.hist_a[:D] == 0).all() and tb.hist_a[D:].abs().sum() > 0 and torch.isfinite(tb.v).all()
+    # teacher-forced replay of step t from the stored observations (rollout-mode history, O_b critic slots)
+    oxy = env.boundary_xy.float()
+    o_count = torch.clamp(env.boundary_count, max=env.O)
+    enc = m.actor.shared_net
+    with torch.no_grad():
+        ha = torch.zeros(2, B * N, E, device="cuda")
+        hc = torch.zeros(2, B * N, E, device="cuda")
+        for t in range(T):
+            graph = ops.GraphBatch(tb.p[t].contiguous(), tb.e[t].contiguous(), oxy, env.map_id, o_count,
+                                   tb.p_adj_bits[t].contiguous(), tb.e_adj[t].contiguous(), tb.o_adj_bits[t].contiguous())
+            hist = []
+            for k in range(D):
+                back, src = k // 2 + 1, (tb.hist_c if k % 2 == 0 else tb.hist_a)
+                hist.append(src[t - back + D] if t - back >= 0 else torch.zeros(B, N, E, device="cuda"))
+            ea = enc.encode(graph, False, hist)
+            fa, ha = m.actor.features(ea.view(1, B * N, E), ha)
+            ec = enc.encode(graph, True, hist)
+            fc, hc = m.critic.features(ec.view(1, B * N, E), hc)
+            w_eff, _ = m.critic.head_weight()
+            torch.testing.assert_close(ea, tb.hist_a[t + D], rtol=1e-6, atol=1e-6)
+            torch.testing.assert_close(ec, tb.hist_c[t + D], rtol=1e-6, atol=1e-6)
+            val = torch.nn.functional.linear(fc[0], w_eff, m.critic.Mean.bias).view(B, N)
+            torch.testing.assert_close(val, tb.v[t], rtol=1e-5, atol=1e-6)
+            lp = torch.log_softmax(torch.nn.functional.linear(fa[0], m.actor.Mean.weight, m.actor.Mean.bias), -1)
+            torch.testing.assert_close(lp.gather(-1, tb.a[t].long().view(-1, 1)).view(B, N), tb.logp[t], rtol=1e-5, atol=2e-6)
+    # training on the rollout: first-epoch ratios are NOT 1 in this algorithm (rollout != training forward, SURVEY 7.4-5)
+    before = [p.detach().clone() for p in m.ac_parameters]
+    objC, objA, ag, cg = m.train(tb, total_steps=B * T)
+    assert np.isfinite(objC) and np.isfinite(objA)
+    assert all(g is not None and np.isfinite(g).all() for g in ag + cg)
+    assert float(m.ac_optimizer.flat_grad.norm()) <= 5.0 + 1e-4
+    m.ac_optimizer.step()
+    assert any(not torch.equal(a, b) for a, b in zip(before, m.ac_parameters))
+
+
+def test_explore_env_reference_signature():
+    """MAPPO.explore_env(env, n) with the single-env facade returns (float, ReplayBuffer, steps) in the reference's
+    buffer layout, and the result trains."""
+    import random
+    from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
+    from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import Pursuit_Env
+    from distributed_multi_agent_reinforcement_learning_b200.replay_buffer import BigBuffer
+    N, T, E, D = 4, 9, 32, 1
+    cfg = _cfg(D, N, T, E)
+    random.seed(4); np.random.seed(4); torch.manual_seed(4)
+    env = Pursuit_Env(cfg)
+    worker = MAPPO(cfg, None, None, "Worker")
+    big = BigBuffer()
+    for _ in range(2):
+        r, buf, steps = worker.explore_env(env, 1)
+        assert steps == T and isinstance(r, float)
+        big.concat_buffer(buf)
+    O = cfg.map.num_max_obstacle
+    shapes = {k: tuple(v.shape) for k, v in big.buffer.items()}
+    assert shapes == dict(p_state=(2, T, N, 4), e_state=(2, T, 1, 4), o_state=(2, T, O, 4), p_adj=(2, T, N, N),
+                          e_adj=(2, T, N, 1), o_adj=(2, T, N, O), actor_historical_embedding=(2, T + D, N, E),
+                          critic_historical_embedding=(2, T + D, N, E), v_n=(2, T + 1, N), a_n=(2, T, N),
+                          a_logprob_n=(2, T, N), r=(2, T, N), active=(2, T, N))
+    assert (big.buffer["p_adj"][..., 1] == 1).all() and (big.buffer["active"] == 1).all()
+    assert worker.reward_norm.running_ms.n == 2 * T            # the estimate persists across episodes
+    learner = MAPPO(cfg, 2, 1, "Learner")
+    learner.actor.set_weights(worker.actor.get_weights())
+    learner.critic.set_weights(worker.critic.get_weights())
+    objC, objA, ag, cg = learner.train(big, 2 * T)
+    assert np.isfinite(objC) and np.isfinite(objA) and len(ag) == len(list(learner.actor.parameters()))
