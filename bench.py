@@ -4,16 +4,16 @@
 Workload (BASELINE.json configs[1]): pursuit-evasion with obstacles, 8 pursuers + 1 A*-driven evader, 60x55 map,
 O=176, T=150 steps, 4096 batched envs per B200.  One bench "step" = one whole closed-loop episode of all envs:
 per env step  evader A* / waypoint step -> observe (comm adjacency, LoS, obstacle visibility) -> pursuer step ->
-reward-norm -> store into the time-major rollout arena.  Actions come from the device-side counter generator
-(scripted policy stand-in; the actor/critic network is not in this loop yet — stated in `config.policy`).
+actor encoder -> critic encoder -> GRU -> heads (sample / log-prob / value) -> reward-norm -> store into the time-major
+rollout arena, i.e. MAPPO.run_episode (DHGN/mappo_parallel.py:742-827) for all envs at once.
 
 metric = agent-env-steps/s = B*N*T / time, whole job (all ranks).
-  value : episode replayed from HBM-resident initial state (CUDA graph of 2*T/10 kernel launches: one A* replanning
-          launch + one fused 10-step rollout launch per replanning period).
+  value : episode replayed from HBM-resident initial state (one CUDA graph of the whole episode).
+  env_only / train : secondary numbers (env-only closed loop with scripted random actions; one PPO epoch).
   e2e   : same episode through the public API with HOST buffers: pinned initial states/targets H2D + episode
           reward sums D2H inside the timed region.
---impl reference : the CPU oracle port of the same loop (oracle/marl_oracle.c, all host threads) on a bounded
-          sample of the same workload.
+--impl reference : the CPU port of the same loop (oracle/marl_oracle.c env with OpenMP + the torch-CPU restatement of
+          the networks, all host threads) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -38,9 +38,9 @@ def workload_config(n_gpus):
     return {"workload": "pursuit_evasion_obstacles_8p_gru_c2", "num_pursuers": N_AGENTS, "envs_per_gpu": B_PER_GPU,
             "global_envs": B_PER_GPU * n_gpus, "max_steps": T_STEPS, "map": "60x55", "num_max_obstacle": 176,
             "map_pool_per_gpu": N_MAPS, "evader": "gpu A* (replan every 10 steps)",
-            "policy": "uniform random actions from a device counter RNG (network not in the loop this round)",
+            "policy": "DHGN actor + critic (embedding 128, depth 1, 2-layer GRU) in the loop, random-init weights, fp32",
             "parallelism": f"dp{n_gpus} (independent env shards, no data-path collective)",
-            "stream_groups": STREAM_GROUPS, "l2": "flushed between timed iterations (256 MiB write)"}
+            "l2": "flushed between timed iterations (256 MiB write)"}
 
 
 def make_cfg():
@@ -155,39 +155,190 @@ def cpu_rollout(cfg, wl, n_envs, steps_T, seed):
     return dt, B * N * steps_T
 
 
+def _reference_weights(cfg, seed=0xB200):
+    """Random-init weights of the reference architecture as a name->tensor dict (same initialisers and order as the
+    reference: orthogonal Linear layers, default nn.GRU init, spectral-norm buffers)."""
+    import torch
+    import torch.nn as nn
+    a = cfg.algo
+    E, D = a.embedding_dim, a.depth
+    torch.manual_seed(seed)
+
+    def lin(i, o):
+        layer = nn.Linear(i, o)
+        nn.init.orthogonal_(layer.weight)
+        nn.init.constant_(layer.bias, 0)
+        return layer
+
+    w = {}
+
+    def put(prefix, layer):
+        w[prefix + ".weight"], w[prefix + ".bias"] = layer.weight.detach(), layer.bias.detach()
+
+    enc = {"semantic_layer": lin(3 * E + 4, E)}
+    for r in range(3):
+        enc[f"MSG_layers.{r}"] = lin(8 if r == 0 else 4, E)
+    for k in range(D):
+        enc[f"FCRA_layers.{k}"] = lin(2 * E, E)
+    enc["AGG_layers.AGG_vertex_0"] = lin(E, E)
+    for k in range(D):
+        enc[f"AGG_layers.AGG_fcra_{k}"] = lin(E, E)
+    for net in ("actor", "critic"):
+        for name, layer in enc.items():
+            put(f"{net}.shared_net.{name}", layer)
+        gru = nn.GRU(E, E, a.num_layers)
+        for k, v in gru.state_dict().items():
+            w[f"{net}.GRU.{k}"] = v
+        if net == "actor":
+            put("actor.Mean", lin(E, cfg.env.action_dim))
+        else:
+            head = lin(E, 1)
+            w["critic.Mean.weight_orig"], w["critic.Mean.bias"] = head.weight.detach(), head.bias.detach()
+            w["critic.Mean.weight_u"] = torch.nn.functional.normalize(torch.randn(1), dim=0)
+    return w
+
+
+def cpu_policy_rollout(cfg, wl, n_envs, steps_T, seed=0):
+    """The reference rollout body (DHGN/mappo_parallel.py:758-801) on the host: oracle C env (observe, A* evader, step,
+    reward-norm; OpenMP) + the torch-CPU restatement of both networks (oracle/policy_ref.py), dense tensors as in the
+    reference.  Returns (seconds, agent_env_steps)."""
+    import numpy as np
+    import torch
+    from oracle import oracle as orc, policy_ref
+    from distributed_multi_agent_reinforcement_learning_b200 import env_params_dict, maps
+    p = orc.EnvParams.from_dict(env_params_dict(cfg))
+    B, N, O, M = n_envs, p.N, p.O, wl["grids"].shape[0]
+    E, D, L = cfg.algo.embedding_dim, cfg.algo.depth, cfg.algo.num_layers
+    beam = maps.beam_directions(p.sensor_beams)
+    raser = np.zeros((M, p.W * p.H, O), np.uint8)
+    ob_count = np.zeros(M, np.int32)
+    oxy = np.zeros((M, O, 4), np.float32)
+    for m in sorted(set(int(v) for v in wl["map_id"][:B])):
+        b_, xy, n = orc.boundary_map(p, wl["grids"][m])
+        n = min(n, O)
+        ob_count[m] = n
+        raser[m, :, :n] = orc.raser_map(p, b_, xy[:n], beam).reshape(p.W * p.H, -1)
+        oxy[m, :n, :2] = xy[:n]
+    st = dict(p_state=wl["p_state"][:B].copy(), e_state=wl["e_state"][:B].copy(), target=wl["target"][:B].copy(),
+              path=np.zeros((B, 512, 2), np.int16), path_len=np.zeros(B, np.int32),
+              grid=np.ascontiguousarray(wl["grids"]), inflated=np.ascontiguousarray(wl["inflated"]), raser=raser,
+              ob_count=ob_count, map_id=wl["map_id"][:B].copy(), action_table=maps.action_table(cfg.defender.vmax),
+              tape=np.ascontiguousarray(wl["tape"][:B]), tape_pos=np.zeros(B, np.int32),
+              p_adj=np.zeros((B, N, N), np.uint8), o_adj=np.zeros((B, N, O), np.uint8), e_adj=np.zeros((B, N), np.uint8),
+              reward=np.zeros((B, N), np.int32), can_apply=np.zeros((B, N), np.uint8), collision=np.zeros(B, np.uint8),
+              time_step=np.zeros(B, np.int32), done=np.zeros(B, np.uint8), wf_n=np.zeros(B, np.int64),
+              wf_mean=np.zeros((B, N)), wf_S=np.zeros((B, N)), wf_std=np.zeros((B, N)),
+              r_norm=np.zeros((B, N), np.float32), status=np.zeros(B, np.int32))
+    w = _reference_weights(cfg)
+    mid = torch.from_numpy(st["map_id"]).long()
+    o_ten = torch.from_numpy(oxy)[mid]                                                     # [B,O,4]
+    o_real = (torch.arange(O)[None, :] < torch.from_numpy(ob_count)[mid][:, None]).float()   # [B,O]
+    gen = torch.Generator().manual_seed(seed)
+    ha, hc = torch.zeros(L, B * N, E), torch.zeros(L, B * N, E)
+    emb_a_prev, emb_c_prev = [], []
+    zero = torch.zeros(B, N, E)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for t in range(steps_T):
+            orc.observe_batch(p, st)
+            obs = dict(p=torch.from_numpy(st["p_state"]).float(), e=torch.from_numpy(st["e_state"]).float().unsqueeze(1),
+                       o=o_ten, p_adj=torch.from_numpy(st["p_adj"]).float(), e_adj=torch.from_numpy(st["e_adj"]).float().unsqueeze(-1),
+                       o_adj=torch.from_numpy(st["o_adj"]).float(), o_real=o_real)
+            hist = []
+            for k in range(D):          # aliased history list: C(t-1), A(t-1), C(t-2), ...
+                back, src = k // 2 + 1, (emb_c_prev if k % 2 == 0 else emb_a_prev)
+                hist.append(src[-back] if len(src) >= back else zero)
+            a, lp, val, ea, ec, ha, hc = policy_ref.rollout_step(w, obs, hist, ha, hc, D, L, generator=gen)
+            emb_a_prev.append(ea)
+            emb_c_prev.append(ec)
+            emb_a_prev, emb_c_prev = emb_a_prev[-(D // 2 + 1):], emb_c_prev[-(D // 2 + 1):]
+            st["action"] = np.ascontiguousarray(a.numpy().astype(np.int32))
+            orc.rollout_iteration_closed(p, st)
+    dt = time.perf_counter() - t0
+    assert not st["status"].any(), "oracle evader reported an error"
+    return dt, B * N * steps_T
+
+
+def cpu_policy_baseline(cfg, wl, steps_T, budget_s):
+    """Bounded sample of the same workload on the host: sized from a short calibration so one pass is ~budget_s."""
+    import torch
+    from oracle import oracle as orc
+    orc.build()
+    cores = orc.num_threads()
+    torch.set_num_threads(cores)
+    n0 = min(32, len(wl["map_id"]))
+    dt, n = cpu_policy_rollout(cfg, wl, n0, 5)
+    per_env_step = dt / (n0 * 5)
+    n_envs = int(max(8, min(len(wl["map_id"]), budget_s / (per_env_step * steps_T))))
+    dt, n = cpu_policy_rollout(cfg, wl, n_envs, steps_T)
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n_envs} of {B_PER_GPU} envs x {steps_T} steps: oracle/marl_oracle.c env (OpenMP) + torch-CPU "
+                      f"restatement of actor/critic (oracle/policy_ref.py), {cores} threads, {dt:.1f} s"}, n_envs
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as orc
-    orc.build()
     cfg = make_cfg()
-    cores = orc.num_threads()
-    sample = B_PER_GPU    # the C port finishes the whole per-GPU workload in seconds, so the sample is all of it
-    wl = host_workload(cfg, sample, min(N_MAPS, sample), seed=0xB200 + 1)
-    for _ in range(args.warmup):
-        cpu_rollout(cfg, wl, sample, 30, seed=1)
+    wl = host_workload(cfg, 512, min(N_MAPS, 512), seed=0xB200 + 1)
+    base, n_envs = cpu_policy_baseline(cfg, wl, steps_T=30, budget_s=2.0)      # calibration + warm-up
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_policy_rollout(cfg, wl, n_envs, 10)
+    # size the per-step sample so that the whole run stays within a few minutes
+    per_env_step = 1.0 / (base["value"] / N_AGENTS)
+    n_envs = int(max(8, min(512, 8.0 / (per_env_step * T_STEPS))))
     tot_t, tot_n = 0.0, 0
     for k in range(args.steps):
-        dt, n = cpu_rollout(cfg, wl, sample, T_STEPS, seed=2 + k)
+        dt, n = cpu_policy_rollout(cfg, wl, n_envs, T_STEPS, seed=2 + k)
         tot_t += dt
         tot_n += n
     value = tot_n / tot_t
-    desc = f"{sample} of {B_PER_GPU} envs x {T_STEPS} steps per step (same maps/placement rules, closed loop with A* evader)"
+    from oracle import oracle as orc
+    desc = (f"{n_envs} of {B_PER_GPU} envs x {T_STEPS} steps per step: oracle C env (A* evader, OpenMP) + torch-CPU actor/critic "
+            f"restatement, {orc.num_threads()} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "vs_baseline": None, "dtype": "f64 env / f32 networks", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+class PolicyEpisodeGraph:
+    """MAPPO.run_episode for all envs (network in the loop) captured as ONE CUDA graph: per env step
+    observe -> actor encoder -> critic encoder -> GRU cells -> heads (sample, log-prob, value) -> A* replan when due ->
+    fused evader-move/step/reward-norm/store kernel; ~70 kernels per step, no host involvement on replay."""
+
+    def __init__(self, torch, mappo, env, arena, T, seed):
+        from distributed_multi_agent_reinforcement_learning_b200 import _lib
+        self.env, self.snap = env, env.snapshot()
+        mappo.rollout_batched(env, arena, T, seed=seed)           # eager warm-up (cuBLAS handles, kernel attributes)
+        torch.cuda.synchronize()
+        env.restore(self.snap)
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        c0 = _lib.CALLS
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(self.graph, stream=side):
+                self.batch = mappo.rollout_batched(env, arena, T, seed=seed)
+        self.our_launches = _lib.CALLS - c0
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        env.restore(self.snap)
+
+    def replay(self):
+        self.graph.replay()
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from distributed_multi_agent_reinforcement_learning_b200 import _lib
+    from distributed_multi_agent_reinforcement_learning_b200 import _lib, parallel
+    from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
     from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv, EpisodeGraph, RolloutArena
 
     rank = int(os.environ.get("RANK", "0"))
@@ -212,7 +363,10 @@ def run_ours(args):
     env.start_episode()
     arena = RolloutArena(env.params, B, T, dev)
     snap = env.snapshot()
-    graph = EpisodeGraph(env, arena, T, seed=0xB200 + rank, groups=STREAM_GROUPS)
+    torch.manual_seed(0xB200)
+    mappo = MAPPO(cfg, B, max(1, round(B / 10)), "Learner")      # mini_batch = round(workers/10) (main.py:48)
+    mappo.sync_weights(0)
+    pol = PolicyEpisodeGraph(torch, mappo, env, arena, T, seed=0xB200 + rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -220,74 +374,88 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: HBM-resident episode --------------------------------------------------------------------
-    def timed_resident(n_iter):
+    def timed(fn, n_iter, before=None):
         total = 0.0
         for _ in range(n_iter):
-            env.restore(snap)
+            if before is not None:
+                before()
             flush.fill_(1)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            graph.replay()
+            fn()
             e.record()
             e.synchronize()
             total += s.elapsed_time(e)
         return total
 
-    timed_resident(args.warmup)
+    # ---- value: whole episode with the networks in the loop, HBM-resident -----------------------------------
+    restore = lambda: env.restore(snap)
+    timed(pol.replay, args.warmup, restore)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
-    ms_total = timed_resident(args.steps)
+    ms_total = timed(pol.replay, args.steps, restore)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     status = int(env.evader_status.max().item())
     assert status == 0, f"evader status {status}: search overflow or target tape exhausted"
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = parallel.max_over_ranks(ms_total, dev)
     value = world * B * N * T * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: host buffers in, host metrics out ------------------------------------------------------------
+    # ---- e2e: host buffers in, host metrics out ----------------------------------------------------------------
     pin = {k: torch.from_numpy(np.ascontiguousarray(wl[k])).pin_memory() for k in ("p_state", "e_state", "target")}
     ep_reward_host = torch.zeros(B, dtype=torch.int64).pin_memory()
     coll_host = torch.zeros(B, dtype=torch.uint8).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in pin.values())
     d2h = ep_reward_host.numel() * 8 + coll_host.numel()
+    zero_names = ("path_len", "time_step", "collision", "done", "tape_pos", "evader_status", "wf_n", "wf_mean", "wf_S", "wf_std")
 
-    def e2e_episode():
+    def e2e_episode(graph):
         env.p_state.copy_(pin["p_state"], non_blocking=True)
         env.e_state.copy_(pin["e_state"], non_blocking=True)
         env.target.copy_(pin["target"], non_blocking=True)
-        for n_ in ("path_len", "time_step", "collision", "done", "tape_pos", "evader_status", "wf_n", "wf_mean", "wf_S", "wf_std"):
+        for n_ in zero_names:
             getattr(env, n_).zero_()
         graph.replay()
         ep_reward_host.copy_(arena.raw_reward.sum(dim=(0, 2), dtype=torch.int64), non_blocking=True)
         coll_host.copy_(env.collision, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    for _ in range(args.warmup):
-        e2e_episode()
+    timed(lambda: e2e_episode(pol), args.warmup)
     barrier()
-    e2e_ms = 0.0
-    for _ in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        e2e_episode()
-        e.record()
-        e.synchronize()
-        e2e_ms += s.elapsed_time(e)
+    e2e_ms = timed(lambda: e2e_episode(pol), args.steps)
     barrier()
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * N * T * args.steps / (float(t.item()) * 1e-3)
+    e2e_value = world * B * N * T * args.steps / (parallel.max_over_ranks(e2e_ms, dev) * 1e-3)
 
-    # ---- per-kernel durations: CUDA events around every launch of one eager episode (same stream) ----------
+    # ---- secondary: env-only closed loop (scripted random policy), as in the survey's env-only probe ------------
+    env.restore(snap)
+    env_graph = EpisodeGraph(env, arena, T, seed=0xB200 + rank, groups=STREAM_GROUPS)
+    timed(env_graph.replay, 2, restore)
+    barrier()
+    env_ms = parallel.max_over_ranks(timed(env_graph.replay, max(3, args.steps // 2), restore), dev) / max(3, args.steps // 2)
+    env_only = {"value": world * B * N * T / (env_ms * 1e-3), "unit": UNIT, "ms_per_episode": env_ms,
+                "policy": "uniform random actions (device counter RNG)", "stream_groups": STREAM_GROUPS}
+
+    # ---- secondary: MAPPO training samples/s (GAE + 10 sequential minibatches fwd/bwd/clip + all-reduce + Adam) ---
+    env.restore(snap)
+    pol.replay()
+    torch.cuda.synchronize()
+    tb = pol.batch
+
+    def train_epoch():
+        mappo.train(tb, total_steps=B * T, return_numpy=False)
+        mappo.update(B * T)
+
+    train_epoch()
+    barrier()
+    n_train = max(1, min(3, args.steps))
+    tr_ms = parallel.max_over_ranks(timed(train_epoch, n_train), dev) / n_train
+    train = {"samples_per_sec": world * B * T * N / (tr_ms * 1e-3), "unit": "samples/s", "ms_per_epoch": tr_ms,
+             "minibatches": -(-B // mappo.mini_batch_size), "dtype": "f32 (TF32 off)",
+             "allreduce": "1 x SUM over the flat gradient arena (%d floats)" % mappo.ac_optimizer.flat_grad.numel()}
+
+    # ---- per-kernel durations of the env kernels: CUDA events around every launch of one eager env-only episode ----
     env.restore(snap)
     timers = {}
     env.rollout_closed(arena, T, 0, seed=0xB200 + rank, timers=timers)
@@ -297,7 +465,6 @@ def run_ours(args):
         v["avg_us"] = 1e3 * v["total_ms"] / v["launches"]
     env.restore(snap)
     ms_episode = ms_total / args.steps
-    kernel_table["episode_graph_ms"] = ms_episode
     peak, peak_src = measured_peaks()
     rk = kernel_table["rollout_kernel(closed)"]
     steps_per_launch = T / rk["launches"]
@@ -305,29 +472,24 @@ def run_ours(args):
     achieved = alg_bytes / (rk["avg_us"] * 1e-6) / 1e9
     roofline = {"kernel": "rollout_kernel<8,1,closed> (observe + evader move + step + reward-norm + store, %d env steps per launch)" % steps_per_launch,
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "avg_launch_us": rk["avg_us"], "share_of_step": rk["total_ms"] / sum(v["total_ms"] for k, v in kernel_table.items() if isinstance(v, dict)),
-                "note": "118 B/agent-step (SURVEY 8d) x 32768 agents x 10 steps per launch; working set of one launch fits L2, "
-                        "so this kernel is latency-bound (fp64 RK4 division chains), not HBM-bound, at 4096 envs"}
+                "traffic": 8.66e6, "traffic_source": "profiles/r1_rollout_kernel_ncu_raw.csv (dram read+write per 10-step launch)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": rk["avg_us"],
+                "share_of_env_only_episode": rk["total_ms"] / env_ms, "share_of_step": rk["total_ms"] / ms_episode,
+                "note": "118 B/agent-step (SURVEY 8d) x 32768 agents x 10 steps per launch.  One launch's working set (38 MB) "
+                        "lives in the 126 MB L2 and the kernel issues ~2400 warp-instructions per warp-step (exact fp64 RK4 "
+                        "with true divisions), so at 4096 envs it is issue/latency-bound, not HBM-bound; with the networks in "
+                        "the loop the step is dominated by the policy kernels and GEMMs"}
 
     if rank == 0:
-        # ---- CPU baseline: oracle port on the box's host cores, bounded sample ------------------------------
-        from oracle import oracle as orc
-        orc.build()
-        cores = orc.num_threads()
-        sample = B       # whole per-GPU workload: a few seconds of CPU work on all host threads
-        wl_cpu = {k: (v[:sample] if k in ("p_state", "e_state", "target", "map_id", "tape") else v) for k, v in wl.items()}
-        cpu_rollout(cfg, wl_cpu, sample, 10, seed=1)
-        dt, n = cpu_rollout(cfg, wl_cpu, sample, T, seed=2)
-        cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {sample} of {B} envs x {T} steps, oracle/marl_oracle.c with OpenMP on {cores} threads ({dt:.1f} s)"}
+        # ---- CPU baseline: oracle port (C env + torch-CPU network restatement) on the host cores, bounded sample ----
+        cpu, _ = cpu_policy_baseline(cfg, wl, steps_T=T, budget_s=12.0)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "dtype": "f64 env / f32 networks", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": graph.launches_per_replay * args.steps, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "kernel_ms_per_episode": kernel_table}))
+            "gpu_launches": pol.our_launches * args.steps, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "env_only": env_only, "train": train, "kernel_ms_per_env_only_episode": kernel_table}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -114,7 +114,12 @@ def lib():
     return _lib
 
 
+CALLS = 0   # successful C-ABI calls so far (each launches >= 1 of our kernels); bench.py reports the delta
+
+
 def check(rc, what=""):
+    global CALLS
+    CALLS += 1
     if rc != MARL_OK:
         msg = lib().marl_last_error_string().decode("utf-8", "replace")
         raise MarlError(f"{what or 'marl call'} failed (code {rc}): {msg}")

@@ -451,6 +451,24 @@ class MAPPO:
             return obj_c / n_updates, obj_a / n_updates, self.actor.get_gradients(), self.critic.get_gradients()
         return obj_c / n_updates, obj_a / n_updates, None, None
 
+    # ------------------------------------------------------------------------------------------------ data parallel
+    def sync_weights(self, src=0):
+        """All replicas start from rank `src`'s weights (main.py:73-75) — one broadcast of the flat parameter arena."""
+        from . import parallel
+        parallel.broadcast_(self.ac_optimizer.flat_param, src)
+        if self.sn:
+            parallel.broadcast_(self.critic.Mean.weight_u, src)
+            parallel.broadcast_(self.critic.Mean.weight_v, src)
+
+    def update(self, total_steps, mean=False):
+        """Learner.set_gradients_and_update across replicas (main.py:121-129, runner.py:72-78): ONE all-reduce (SUM) of
+        the flat gradient arena over NCCL, then the same fused Adam step on every replica."""
+        from . import parallel
+        parallel.allreduce_sum_(self.ac_optimizer.flat_grad, mean=mean)
+        self.ac_optimizer.step()
+        if self.use_lr_decay:
+            self.lr_decay(total_steps)
+
     def lr_decay(self, total_steps):
         lr_now = self.lr * (1 - total_steps / self.max_train_steps)
         for p in self.ac_optimizer.param_groups:

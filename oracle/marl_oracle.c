@@ -557,6 +557,31 @@ void orc_rollout_iteration_closed(const marl_env_params *p, int32_t B, double *p
     }
 }
 
+/* communicate + sensor for B envs (the observation the policy consumes before it acts), all host threads. */
+void orc_observe_batch(const marl_env_params *p, int32_t B, const double *p_state, const double *e_state,
+                       const uint8_t *grid, const uint8_t *raser, const int32_t *ob_count, int32_t ob_stride,
+                       const int32_t *map_id, uint8_t *p_adj, uint8_t *o_adj, uint8_t *e_adj)
+{
+    int N = p->N, O = p->O, WH = p->W * p->H;
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; b++) {
+        int m = map_id ? map_id[b] : b;
+        const uint8_t *g = grid + (size_t)m * WH;
+        const uint8_t *rs = raser + (size_t)m * WH * ob_stride;
+        const double *ps = p_state + (size_t)b * N * 4, *es = e_state + (size_t)b * 4;
+        orc_communicate(p, ps, p_adj + (size_t)b * N * N);
+        uint8_t *oa = o_adj + (size_t)b * N * O;
+        memset(oa, 0, (size_t)N * O);
+        for (int i = 0; i < N; i++) {
+            int cx = (int)ps[4 * i], cy = (int)ps[4 * i + 1];
+            int ob = ob_count[m] < O ? ob_count[m] : O;
+            memcpy(oa + (size_t)i * O, rs + ((size_t)cx * p->H + cy) * ob_stride, (size_t)ob);
+            e_adj[(size_t)b * N + i] = (uint8_t)orc_find_attacker(p, g, orc_round(ps[4 * i]), orc_round(ps[4 * i + 1]),
+                                                                 orc_round(es[0]), orc_round(es[1]));
+        }
+    }
+}
+
 int32_t orc_num_threads(void)
 {
 #ifdef _OPENMP

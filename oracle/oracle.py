@@ -234,5 +234,13 @@ def rollout_iteration_closed(p, st):
         _p(st["r_norm"]), _p(st["status"]))
 
 
+def observe_batch(p, st):
+    """communicate + sensor for all envs of `st` (fills st['p_adj'], st['o_adj'], st['e_adj'])."""
+    B = st["p_state"].shape[0]
+    lib().orc_observe_batch(C.byref(p), C.c_int32(B), _p(st["p_state"]), _p(st["e_state"]), _p(st["grid"]),
+                            _p(st["raser"]), _p(st["ob_count"]), C.c_int32(st["raser"].shape[-1]), _p(st["map_id"]),
+                            _p(st["p_adj"]), _p(st["o_adj"]), _p(st["e_adj"]))
+
+
 def num_threads():
     return lib().orc_num_threads()

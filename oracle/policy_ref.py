@@ -136,3 +136,31 @@ def gae(batch, gamma=0.99, lamda=0.95, T=None):
     v_target = adv + v[:, :-1]
     adv = (adv - adv.mean()) / (adv.std() + 1e-5) * active
     return adv, v_target
+
+
+def rollout_step(w, obs, hist, ha, hc, depth, num_layers=2, generator=None):
+    """One step of MAPPO.run_episode's network part (:773-784) for a batch of envs, dense tensors like the reference:
+    obs = dict(p [B,N,4], e [B,1,4], o [B,O,4], p_adj [B,N,N], e_adj [B,N,1], o_adj [B,N,O], o_real [B,O] 0/1 mask of the
+    O_b real boundary cells); hist = newest-first list of [B,N,E] (the aliased list: C(t-1), A(t-1), C(t-2), ...).
+    Returns (action [B,N], logp, value, emb_a, emb_c, ha, hc)."""
+    p, e, o = obs["p"], obs["e"], obs["o"]
+    B, N = p.shape[:2]
+    E = w["actor.shared_net.semantic_layer.weight"].shape[0]
+    out = {}
+    for net, h in (("actor", ha), ("critic", hc)):
+        if net == "actor":
+            p_adj, e_adj, o_adj = obs["p_adj"], obs["e_adj"], obs["o_adj"]
+        else:   # all ones over the O_b REAL cells only: o_ten is unpadded during rollout (:756-757,774)
+            p_adj, e_adj = torch.ones_like(obs["p_adj"]), torch.ones_like(obs["e_adj"])
+            o_adj = obs["o_real"].unsqueeze(1).expand(B, N, -1).contiguous()
+        h0 = dhgn_encoder(w, net, p, e, o, p_adj, e_adj, o_adj)
+        emb = dhgn_fcra(w, net, h0, hist, p_adj)
+        feat, hn = gru(w, f"{net}.GRU", emb.reshape(1, B * N, E), h, num_layers)
+        out[net] = (emb, feat[0], hn)
+    logits = F.linear(out["actor"][1], w["actor.Mean.weight"], w["actor.Mean.bias"])
+    dist = torch.distributions.Categorical(probs=torch.softmax(logits, -1))
+    a = dist.sample() if generator is None else torch.multinomial(dist.probs, 1, generator=generator)[:, 0]
+    Weff, _, _ = critic_head_weight(w)
+    val = F.linear(out["critic"][1], Weff, w["critic.Mean.bias"])[:, 0]
+    return (a.view(B, N), dist.log_prob(a).view(B, N), val.view(B, N), out["actor"][0], out["critic"][0],
+            out["actor"][2], out["critic"][2])
