@@ -104,10 +104,12 @@ class DHGN(nn.Module):
         S, N, E = graph.S, graph.N, self.embedding_dim
         m = self.MSG_layers
         agg = ops.message_agg(graph, all_ones, m[0].weight, m[0].bias, m[1].weight, m[1].bias, m[2].weight, m[2].bias)
-        av = self.AGG_layers["AGG_vertex_0"]
-        emb3 = torch.relu(torch.addmm(av.bias, agg.view(S * N * 3, E), av.weight.t())).view(S * N, 3 * E)
-        h = torch.addmm(self.semantic_layer.bias, torch.cat([graph.p.view(S * N, 4), emb3], dim=1),
-                        self.semantic_layer.weight.t())
+        av, sem = self.AGG_layers["AGG_vertex_0"], self.semantic_layer
+        emb3 = ops.linear(agg.view(S * N * 3, E), av.weight, av.bias, relu=True).view(S * N, 3 * E)
+        # semantic layer on [p | emb0 | emb1 | emb2] without materialising the concatenation: the 4-wide state part is
+        # a rank-4 update handed to the GEMM as its additive input
+        p_term = torch.addmm(sem.bias, graph.p.view(S * N, 4), sem.weight[:, :4].t())
+        h = ops.linear(emb3, sem.weight[:, 4:], None, add=p_term)
         for k in range(self.depth):
             hk = hist[k]
             if isinstance(hk, tuple):
@@ -115,8 +117,8 @@ class DHGN(nn.Module):
             else:
                 nb = ops.fcra_agg(hk, graph.p_adj_bits, all_ones, S, N, E)
             af, ff = self.AGG_layers[f"AGG_fcra_{k}"], self.FCRA_layers[k]
-            mk = torch.relu(torch.addmm(af.bias, nb.view(S * N, E), af.weight.t()))
-            h = torch.relu(torch.addmm(ff.bias, torch.cat([mk, h], dim=1), ff.weight.t()))
+            mk = ops.linear(nb.view(S * N, E), af.weight, af.bias, relu=True)
+            h = ops.linear(mk, ff.weight, ff.bias, relu=True, x2=h)      # FCRA_k([m_k | h]) without the concatenation
         return h.view(S, N, E)
 
     # reference signature: forward(attributes: DataLoader, historical_embeddings: DataLoader)

@@ -49,6 +49,81 @@ def pack_bits(dense):
     return w.to(torch.int32).contiguous()
 
 
+# ---------------------------------------------------------------------------------------------------- dense layers
+USE_TENSOR_CORES = True    # 3xTF32 tcgen05 GEMM for the E-wide layers (fp32-level accuracy); False -> library sgemm
+
+
+def _tc_ok(x, W, x2):
+    N, K = W.shape
+    K1 = x.shape[1]
+    return (USE_TENSOR_CORES and x.is_cuda and x.dtype == torch.float32 and N % 128 == 0 and K1 % 32 == 0
+            and (K - K1) % 32 == 0 and W.stride(1) == 1 and W.stride(0) % 4 == 0 and W.data_ptr() % 16 == 0)
+
+
+def _gemm_tc(x, x2, W, bias, add, relu, out=None):
+    """C = act(x W[:, :K1]^T + x2 W[:, K1:]^T + bias + add) through marl_gemm_tf32x3."""
+    M, K1 = x.shape
+    N, K = W.shape
+    x = x if (x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0) else x.contiguous()
+    if x2 is not None:
+        x2 = x2 if (x2.stride(1) == 1 and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0) else x2.contiguous()
+    if add is not None:
+        add = add if (add.stride(1) == 1 and add.stride(0) % 4 == 0 and add.data_ptr() % 16 == 0) else add.contiguous()
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    _lib.check(_L().marl_gemm_tf32x3(
+        M, N, K1, K - K1, x.data_ptr(), x.stride(0), x2.data_ptr() if x2 is not None else None,
+        x2.stride(0) if x2 is not None else 0, W.data_ptr(), W.stride(0), bias.data_ptr() if bias is not None else None,
+        add.data_ptr() if add is not None else None, add.stride(0) if add is not None else 0, out.data_ptr(), N,
+        1 if relu else 0, _lib.stream_ptr()), "marl_gemm_tf32x3")
+    return out
+
+
+class _LinearTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, x2, W, bias, add, relu):
+        out = _gemm_tc(x, x2, W, bias, add, relu)
+        ctx.relu = relu
+        ctx.has = (x2 is not None, bias is not None, add is not None)
+        ctx.save_for_backward(x, x2, W, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, x2, W, out = ctx.saved_tensors
+        has_x2, has_bias, has_add = ctx.has
+        if ctx.relu:
+            dy = dy * (out > 0)
+        dy = dy.contiguous()
+        K1 = x.shape[1]
+        need = ctx.needs_input_grad
+        dx = dx2 = dW = db = dadd = None
+        if need[0]:   # dX = dY W[:, :K1]: same kernel with the transposed weight slice as "W"
+            Wt = W[:, :K1].t().contiguous()
+            dx = _gemm_tc(dy, None, Wt, None, None, False) if _tc_ok(dy, Wt, None) else dy @ W[:, :K1]
+        if has_x2 and need[1]:
+            Wt2 = W[:, K1:].t().contiguous()
+            dx2 = _gemm_tc(dy, None, Wt2, None, None, False) if _tc_ok(dy, Wt2, None) else dy @ W[:, K1:]
+        if need[2]:   # weight gradient: reduction over the (huge) row dimension, library GEMM
+            dW = torch.cat([dy.t() @ x, dy.t() @ x2], dim=1) if has_x2 else dy.t() @ x
+        if has_bias and need[3]:
+            db = dy.sum(0)
+        if has_add and need[4]:
+            dadd = dy
+        return dx, dx2, dW, db, dadd, None
+
+
+def linear(x, W, bias=None, relu=False, x2=None, add=None):
+    """act(cat([x, x2], 1) @ W.T + bias + add) for 2-D x; tensor-core path when the shape allows, library GEMM otherwise."""
+    if _tc_ok(x, W, x2):
+        return _LinearTC.apply(x, x2, W, bias, add, relu)
+    xin = x if x2 is None else torch.cat([x, x2], dim=1)
+    out = torch.addmm(bias, xin, W.t()) if bias is not None else xin @ W.t()
+    if add is not None:
+        out = out + add
+    return torch.relu(out) if relu else out
+
+
 class _MessageAgg(torch.autograd.Function):
     @staticmethod
     def forward(ctx, graph, all_ones, W0, b0, W1, b1, W2, b2):
@@ -97,7 +172,11 @@ class _GRULayer(torch.autograd.Function):
         T, R, E = x.shape
         need = any(ctx.needs_input_grad)
         x = x.contiguous()
-        gi_all = torch.addmm(b_ih, x.view(T * R, E), w_ih.t()).view(T, R, 3 * E)
+        tc = _tc_ok(x.view(T * R, E), w_ih, None) and _tc_ok(x.view(T * R, E), w_hh, None)
+        if tc:
+            gi_all = _gemm_tc(x.view(T * R, E), None, w_ih, b_ih, None, False).view(T, R, 3 * E)
+        else:
+            gi_all = torch.addmm(b_ih, x.view(T * R, E), w_ih.t()).view(T, R, 3 * E)
         out = torch.empty(T, R, E, dtype=x.dtype, device=x.device)
         saves = torch.empty(4, T, R, E, dtype=x.dtype, device=x.device) if need else None
         gh = torch.empty(R, 3 * E, dtype=x.dtype, device=x.device)
@@ -105,7 +184,10 @@ class _GRULayer(torch.autograd.Function):
         h = h0.contiguous()
         L, P, st = _L(), _lib.ptr, _lib.stream_ptr()
         for t in range(T):
-            torch.addmm(b_hh, h, w_hh_t, out=gh)
+            if tc:
+                _gemm_tc(h, None, w_hh, b_hh, None, False, out=gh)
+            else:
+                torch.addmm(b_hh, h, w_hh_t, out=gh)
             sv = [saves[k, t].data_ptr() for k in range(4)] if need else [None] * 4
             _lib.check(L.marl_gru_cell_fwd(R, E, gi_all[t].data_ptr(), P(gh), h.data_ptr(), out[t].data_ptr(), *sv, st),
                        "marl_gru_cell_fwd")
@@ -126,6 +208,8 @@ class _GRULayer(torch.autograd.Function):
         dh_prev = torch.empty_like(dh)
         h0c = h0.contiguous()
         L, st = _L(), _lib.stream_ptr()
+        w_hh_T = w_hh.t().contiguous()                      # [E,3E]: "weight" of the dh_{t-1} += dgh_t @ W_hh projection
+        tc = _tc_ok(dgh[0], w_hh_T, None)
         for t in range(T - 1, -1, -1):
             torch.add(d_out[t], dh, out=dh_tot)
             hp = out[t - 1] if t > 0 else h0c
@@ -133,10 +217,14 @@ class _GRULayer(torch.autograd.Function):
                                            saves[2, t].data_ptr(), saves[3, t].data_ptr(), hp.data_ptr(),
                                            dgi[t].data_ptr(), dgh[t].data_ptr(), dh_prev.data_ptr(), st),
                        "marl_gru_cell_bwd")
-            torch.addmm(dh_prev, dgh[t], w_hh, out=dh)          # dh_{t-1} = dh_t*z + dgh_t @ W_hh
+            if tc:                                            # dh_{t-1} = dh_t*z + dgh_t @ W_hh
+                _gemm_tc(dgh[t], None, w_hh_T, None, dh_prev, False, out=dh)
+            else:
+                torch.addmm(dh_prev, dgh[t], w_hh, out=dh)
         dgi2, dgh2 = dgi.view(T * R, 3 * E), dgh.view(T * R, 3 * E)
         h_prev_all = torch.cat([h0c.unsqueeze(0), out[:-1]], dim=0).view(T * R, E)
-        dx = torch.mm(dgi2, w_ih).view(T, R, E)
+        w_ih_T = w_ih.t().contiguous()
+        dx = (_gemm_tc(dgi2, None, w_ih_T, None, None, False) if _tc_ok(dgi2, w_ih_T, None) else torch.mm(dgi2, w_ih)).view(T, R, E)
         return dx, dh.clone(), torch.mm(dgi2.t(), x.view(T * R, E)), torch.mm(dgh2.t(), h_prev_all), dgi2.sum(0), dgh2.sum(0)
 
 

@@ -250,6 +250,15 @@ int marl_act_head(int64_t R, int32_t E, int32_t A, const float *d_feat_a, const 
                   const float *d_ba, const float *d_wc_eff, const float *d_bc, uint64_t seed, int32_t t,
                   int32_t deterministic, int32_t *d_action, float *d_action_f32, float *d_logp, float *d_value,
                   void *stream);
+/* Dense layer on the tcgen05 tensor cores with fp32-level accuracy (3xTF32 split, fp32 accumulation in TMEM):
+ * C[M,N] = act(A1[M,K1] W[:, :K1]^T + A2[M,K2] W[:, K1:]^T + bias[N] + D[M,N]), W = nn.Linear weight [N, K1+K2] row-major.
+ * Replaces the library sgemm behind every E-wide nn.Linear / GRU projection of DHGN/mappo_parallel.py:116-545.  The
+ * second operand pair stands in for torch.concatenate([a, b], -1) (:232), D for the 4-wide state part of the semantic
+ * layer (:286,303).  Requires N % 128 == 0, K1 % 32 == 0, K2 % 32 == 0, 16-byte aligned rows. */
+int marl_gemm_tf32x3(int32_t M, int32_t N, int32_t K1, int32_t K2, const float *d_A1, int64_t lda1, const float *d_A2,
+                     int64_t lda2, const float *d_W, int64_t ldw, const float *d_bias, const float *d_D, int64_t ldd,
+                     float *d_C, int64_t ldc, int32_t relu, void *stream);
+
 /* torch.nn.utils.clip_grad_norm_ (:710-711) and torch.optim.Adam.step (runner.py:72-78) on flat fp32 arenas. */
 int64_t marl_clip_workspace_bytes(int64_t n);
 int marl_clip_grad_norm(int64_t n, float *d_grad, float max_norm, void *d_workspace, float *d_total_norm, void *stream);
