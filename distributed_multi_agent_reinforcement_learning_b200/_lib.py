@@ -87,6 +87,10 @@ _PROTOTYPES = {
     "marl_gae_workspace_bytes": (_I64, [_I32, _I32, _I32]),
     "marl_gae": (C.c_int, [_I32, _I32, _I32, _VP, _VP, _VP, _I32, _F32, _F32, _I32, _VP, _VP, _VP, _VP]),
     "marl_gather_rows": (C.c_int, [_VP, _VP, _VP, _I32, _I64, _I64, _VP]),
+    "marl_env3d_step": (C.c_int, [_VP, _I32] + [_VP] * 10),
+    "marl_env3d_evader_step": (C.c_int, [_VP, _I32] + [_VP] * 4),
+    "marl_env3d_adjacency": (C.c_int, [_VP, _I32] + [_VP] * 8),
+    "marl_env3d_rollout": (C.c_int, [_VP, _I32, _I32, _I32, _I32] + [_VP] * 8 + [_U64, _VP, _VP]),
     "marl_rollout_steps": (C.c_int, [_PP, _I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _U64, _VP, _VP, _VP, _VP, _VP,
                                      _VP, _VP, _VP, _VP, _VP, C.POINTER(RolloutRecords), _VP]),
 }

@@ -26,7 +26,7 @@ int check_launch(const char *what)
 }
 
 // largest double s with sqrt(s) <= r  (strict=false)  or  sqrt(s) < r  (strict=true)
-static double sq_threshold(double r, bool strict)
+double sq_threshold(double r, bool strict)
 {
     auto ok = [&](double s) { double q = sqrt(s); return strict ? (q < r) : (q <= r); };
     double s = r * r;

@@ -206,6 +206,55 @@ int marl_rollout_closed(const marl_env_params *p, int32_t B, int32_t B_stride, i
                         uint8_t *d_collision, int32_t *d_time_step,
                         const marl_rollout_records *rec, void *stream);
 
+/* ---- 3-D particle env (second env family, BASELINE config 4) --------------------------------------------
+ * Replaces environment/env_3d/particle_env.py: Point.step (:25-57), ParticleEnv.step (:204-217),
+ * reward / agent_reward (:263-279), update_agent_active (:281-321), get_done (:219-238), get_active (:240-244),
+ * get_adj_mat (:323-334), collision_detection (:336-346) and the evader's Point.step inside evader_step (:348-373;
+ * the commanded action itself comes from scipy SLSQP in eva.e_f and is an INPUT here).
+ * Layouts: p_state f64 [B,N,6] (x,y,z,phi,gamma,v), p_active u8 [B,N], e_state f64 [B,6], e_active u8 [B],
+ * target f64 [B,3], actions f64 in [-1,1]^3 (phi, gamma, v commands). */
+typedef struct marl_env3d_params {
+    int32_t N;                 /* p_num */
+    int32_t max_step;          /* ParticleEnv.max_step (200) */
+    double p_vmax, e_vmax;     /* 0.7 / 1 */
+    double kill_radius;        /* 0.5 */
+    double ang_lmt, v_lmt;     /* pi/4, 0.4 */
+    double step_size;          /* 0.5 */
+    double comm_range;         /* p_comm_range 6 (pursuer-pursuer adjacency) */
+    double sen_range;          /* p_sen_range 3 (pursuer-evader adjacency) */
+} marl_env3d_params;
+
+/* One ParticleEnv.step for B envs: time_step += 1; every active pursuer moves; reward from the post-move state
+ * (+1 per active evader within kill_radius, -(active teammates within kill_radius, self included, - 1)); pursuers /
+ * the evader that touch anything are deactivated and parked at (1000,1000,1000,0,0,0); done = evader at target ||
+ * no pursuer alive || evader dead || time_step >= max_step.  In/out: p_state, p_active, e_state, e_active,
+ * time_step.  Out: reward i32 [B,N], done u8 [B]. */
+int marl_env3d_step(const marl_env3d_params *p, int32_t B, double *d_p_state, uint8_t *d_p_active, double *d_e_state,
+                    uint8_t *d_e_active, const double *d_target, const double *d_action, int32_t *d_time_step,
+                    int32_t *d_reward, uint8_t *d_done, void *stream);
+/* The evader's own Point.step (particle_env.py:372) for a commanded action d_e_action f64 [B,3]. */
+int marl_env3d_evader_step(const marl_env3d_params *p, int32_t B, double *d_e_state, const uint8_t *d_e_active,
+                           const double *d_e_action, void *stream);
+/* get_adj_mat for the two relations a policy consumes: pursuer-pursuer within comm_range (rows of inactive pursuers
+ * are zero; columns are not masked, as in the reference) and pursuer-evader within sen_range.
+ * Out: d_pp_adj_bits u32 [B,N,NW], d_pe_adj u8 [B,N]; dense f32 [B,N,N] / [B,N,1] optional (NULL to skip). */
+int marl_env3d_adjacency(const marl_env3d_params *p, int32_t B, const double *d_p_state, const uint8_t *d_p_active,
+                         const double *d_e_state, uint32_t *d_pp_adj_bits, uint8_t *d_pe_adj, float *d_pp_adj_f32,
+                         float *d_pe_adj_f32, void *stream);
+/* K fused iterations of (adjacency -> evader move -> step -> store) with actions from tapes
+ * (d_action_tape f64 [K,B,N,3], d_e_action_tape f64 [K,B,3]) or, when a tape is NULL, from the counter RNG
+ * (uniform in [-1,1), keyed by seed / agent / t).  Time-major records (any may be NULL): p_state_f32 [T,B,N,6],
+ * e_state_f32 [T,B,6], pp_adj_bits [T,B,N,NW], pe_adj u8 [T,B,N], reward i32 [T,B,N], active_f32 [T,B,N]
+ * (active flag BEFORE the step, what a buffer stores), done u8 [T,B]. */
+typedef struct marl_env3d_records {
+    float *p_state_f32; float *e_state_f32; uint32_t *pp_adj_bits; uint8_t *pe_adj; int32_t *reward; float *active_f32;
+    uint8_t *done;
+} marl_env3d_records;
+int marl_env3d_rollout(const marl_env3d_params *p, int32_t B, int32_t T, int32_t t0, int32_t K, double *d_p_state,
+                       uint8_t *d_p_active, double *d_e_state, uint8_t *d_e_active, const double *d_target,
+                       int32_t *d_time_step, const double *d_action_tape, const double *d_e_action_tape, uint64_t seed,
+                       const marl_env3d_records *rec, void *stream);
+
 /* ---- kernel family 5: DHGN actor/critic, the non-GEMM parts (fp32) -----------------------------------------
  * The dense E-wide layers (AGG_vertex_0, semantic_layer, AGG_fcra_k, FCRA_layers.k, GRU weight matrices) are plain
  * library GEMMs on the host side; these entry points fuse everything pairwise / sparse / pointwise around them so that

@@ -590,3 +590,145 @@ int32_t orc_num_threads(void)
     return 1;
 #endif
 }
+
+/* =====================================================================================================
+ * 3-D particle env (environment/env_3d/particle_env.py) — SURVEY §8 a23.  Pinned by tests/golden/env3d_*.npz
+ * (oracle/gen_golden_env3d.py executes the unmodified reference).
+ * ===================================================================================================== */
+
+/* np.linalg.norm of a 3-vector: sqrt(ddot) with the FMA-contracted scalar tail (fma(c,c,fma(b,b,a*a)));
+ * checked against numpy 2.3.5 in the build container on 50 000 random vectors (0 mismatches; the unfused form
+ * mismatches on 5 321 of them). */
+static inline double orc_norm3(double a, double b, double c) { return sqrt(fma(c, c, fma(b, b, a * a))); }
+static inline double orc_clip(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+static inline double orc_sign(double v) { return (v > 0.0) - (v < 0.0); }
+
+/* particle_env.py:25-57 Point.step for an ACTIVE point; s = (x,y,z,phi,gamma,v) */
+void orc_point_step(double *s, const double *a, double v_max, double ang_lmt, double v_lmt, double step_size)
+{
+    const double pi = 3.141592653589793;
+    double phi = a[0] * pi;
+    double gamma = a[1] * pi / 2;
+    double v = (a[2] + 1) / 2 * v_max;
+    double delta_gamma = orc_clip(gamma - s[4], -ang_lmt, ang_lmt);
+    double delta_v = orc_clip(v - s[5], -v_lmt, v_lmt);
+    s[4] += delta_gamma;
+    s[5] += delta_v;
+    double delta_phi;
+    if (orc_sign(phi * s[3]) >= 0) {
+        delta_phi = orc_clip(phi - s[3], -ang_lmt, ang_lmt);
+    } else {
+        double d = fabs(phi - s[3]);
+        if (d < 2 * pi - d) {
+            delta_phi = orc_clip(phi - s[3], -ang_lmt, ang_lmt);
+        } else {
+            delta_phi = 2 * pi - d;
+            double sign = -orc_sign(phi - s[3]);
+            delta_phi = orc_clip(delta_phi, 0, ang_lmt) * sign;
+        }
+    }
+    s[3] += delta_phi;
+    if (s[3] > pi) s[3] -= 2 * pi;
+    else if (s[3] < -pi) s[3] += 2 * pi;
+    s[0] += s[5] * cos(s[4]) * cos(phi) * step_size;   /* commanded phi, updated gamma (:53-55) */
+    s[1] += s[5] * cos(s[4]) * sin(phi) * step_size;
+    s[2] += s[5] * sin(s[4]) * step_size;
+}
+
+static void orc_park(double *s)
+{ /* particle_env.py:303-309 */
+    s[0] = s[1] = s[2] = 1000.0;
+    s[3] = s[4] = s[5] = 0.0;
+}
+
+/* particle_env.py:204-217 step (+ :219-238, :263-321, :336-346) for ONE env */
+void orc_env3d_step(const marl_env3d_params *p, double *ps, uint8_t *pa, double *es, uint8_t *ea, const double *target,
+                    const double *action, int32_t *time_step, int32_t *reward, uint8_t *done)
+{
+    const int N = p->N;
+    *time_step += 1;
+    for (int i = 0; i < N; ++i)
+        if (pa[i]) orc_point_step(ps + 6 * i, action + 3 * i, p->p_vmax, p->ang_lmt, p->v_lmt, p->step_size);
+    /* reward(True): only active evaders / active teammates are visible (get_team_state(rules=True)) */
+    for (int i = 0; i < N; ++i) {
+        int r = 0;
+        if (pa[i]) {
+            const double *s = ps + 6 * i;
+            if (*ea && orc_norm3(s[0] - es[0], s[1] - es[1], s[2] - es[2]) <= p->kill_radius) r += 1;
+            int inner = 0;
+            for (int j = 0; j < N; ++j)
+                if (pa[j]) {
+                    const double *q = ps + 6 * j;
+                    if (orc_norm3(s[0] - q[0], s[1] - q[1], s[2] - q[2]) <= p->kill_radius) inner += 1;
+                }
+            r -= (inner - 1);
+        }
+        reward[i] = r;
+    }
+    /* update_agent_active: all verdicts from the pre-update state, then applied */
+    uint8_t dead[MARL_MAX_AGENTS];
+    uint8_t e_dead = 0;
+    for (int i = 0; i < N; ++i) {
+        dead[i] = 0;
+        if (!pa[i]) continue;
+        const double *s = ps + 6 * i;
+        int c = 0;
+        for (int j = 0; j < N; ++j)
+            if (pa[j]) {
+                const double *q = ps + 6 * j;
+                c += orc_norm3(s[0] - q[0], s[1] - q[1], s[2] - q[2]) <= p->kill_radius;
+            }
+        if (*ea) c += orc_norm3(s[0] - es[0], s[1] - es[1], s[2] - es[2]) <= p->kill_radius;
+        dead[i] = (c - 1) != 0;
+    }
+    if (*ea) {
+        int c = 1; /* itself */
+        for (int j = 0; j < N; ++j)
+            if (pa[j]) {
+                const double *q = ps + 6 * j;
+                c += orc_norm3(es[0] - q[0], es[1] - q[1], es[2] - q[2]) <= p->kill_radius;
+            }
+        e_dead = (c - 1) != 0;
+    }
+    for (int i = 0; i < N; ++i)
+        if (dead[i]) { pa[i] = 0; orc_park(ps + 6 * i); }
+    if (e_dead) { *ea = 0; orc_park(es); }
+    /* get_done */
+    int d = orc_norm3(es[0] - target[0], es[1] - target[1], es[2] - target[2]) <= p->kill_radius;
+    int alive = 0;
+    for (int i = 0; i < N; ++i) alive += pa[i];
+    if (alive == 0) d = 1;
+    if (!*ea) d = 1;
+    *done = (d || *time_step >= p->max_step) ? 1 : 0;
+}
+
+/* particle_env.py:323-334 get_adj_mat: pursuer-pursuer (comm_range) and pursuer-evader (sen_range) */
+void orc_env3d_adjacency(const marl_env3d_params *p, const double *ps, const uint8_t *pa, const double *es,
+                         uint8_t *pp_adj, uint8_t *pe_adj)
+{
+    const int N = p->N;
+    for (int i = 0; i < N; ++i) {
+        const double *s = ps + 6 * i;
+        for (int j = 0; j < N; ++j) {
+            const double *q = ps + 6 * j;
+            pp_adj[i * N + j] = pa[i] && orc_norm3(s[0] - q[0], s[1] - q[1], s[2] - q[2]) <= p->comm_range;
+        }
+        pe_adj[i] = pa[i] && orc_norm3(s[0] - es[0], s[1] - es[1], s[2] - es[2]) <= p->sen_range;
+    }
+}
+
+/* one iteration of the batched loop the CUDA rollout runs: adjacency -> evader move -> step, all envs (OpenMP) */
+void orc_env3d_iteration(const marl_env3d_params *p, int32_t B, double *ps, uint8_t *pa, double *es, uint8_t *ea,
+                         const double *target, const double *action, const double *e_action, int32_t *time_step,
+                         int32_t *reward, uint8_t *done, uint8_t *pp_adj, uint8_t *pe_adj)
+{
+    const int N = p->N;
+#pragma omp parallel for schedule(static)
+    for (int32_t b = 0; b < B; ++b) {
+        orc_env3d_adjacency(p, ps + (size_t)b * N * 6, pa + (size_t)b * N, es + (size_t)b * 6,
+                            pp_adj + (size_t)b * N * N, pe_adj + (size_t)b * N);
+        if (ea[b]) orc_point_step(es + (size_t)b * 6, e_action + (size_t)b * 3, p->e_vmax, p->ang_lmt, p->v_lmt, p->step_size);
+        orc_env3d_step(p, ps + (size_t)b * N * 6, pa + (size_t)b * N, es + (size_t)b * 6, ea + b, target + (size_t)b * 3,
+                       action + (size_t)b * N * 3, time_step + b, reward + (size_t)b * N, done + b);
+    }
+}

@@ -244,3 +244,59 @@ def observe_batch(p, st):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+# ---------------------------------------------------------------------------------------------- 3-D particle env
+class Env3dParams(C.Structure):
+    """Mirror of marl_env3d_params (include/marl_b200.h)."""
+    _fields_ = [("N", C.c_int32), ("max_step", C.c_int32)] + \
+               [(n, C.c_double) for n in ("p_vmax", "e_vmax", "kill_radius", "ang_lmt", "v_lmt", "step_size",
+                                          "comm_range", "sen_range")]
+
+    @classmethod
+    def from_dict(cls, d):
+        p = cls()
+        for name, ctype in cls._fields_:
+            setattr(p, name, int(d[name]) if ctype is C.c_int32 else float(d[name]))
+        return p
+
+    @classmethod
+    def from_fixture(cls, fx):
+        return cls.from_dict(dict(N=fx["n"], max_step=fx["max_step"], p_vmax=fx["p_vmax"], e_vmax=fx["e_vmax"],
+                                  kill_radius=fx["kill_radius"], ang_lmt=fx["ang_lmt"], v_lmt=fx["v_lmt"],
+                                  step_size=fx["step_size"], comm_range=fx["p_comm_range"], sen_range=fx["p_sen_range"]))
+
+
+def point_step(state, action, v_max, ang_lmt, v_lmt, step_size):
+    s = _c(state, np.float64).copy()
+    a = _c(action, np.float64)
+    lib().orc_point_step(_p(s), _p(a), C.c_double(v_max), C.c_double(ang_lmt), C.c_double(v_lmt), C.c_double(step_size))
+    return s
+
+
+def env3d_step(p, p_state, p_active, e_state, e_active, target, action, time_step):
+    """One ParticleEnv.step for one env -> dict(p_state, p_active, e_state, e_active, reward, done, time_step)."""
+    ps, pa = _c(p_state, np.float64).copy(), _c(p_active, np.uint8).copy()
+    es, ea = _c(e_state, np.float64).copy(), C.c_uint8(int(e_active))
+    tg, act = _c(target, np.float64), _c(action, np.float64)
+    ts, done = C.c_int32(int(time_step)), C.c_uint8(0)
+    reward = np.zeros(p.N, np.int32)
+    lib().orc_env3d_step(C.byref(p), _p(ps), _p(pa), _p(es), C.byref(ea), _p(tg), _p(act), C.byref(ts), _p(reward),
+                         C.byref(done))
+    return dict(p_state=ps, p_active=pa, e_state=es, e_active=ea.value, reward=reward, done=done.value, time_step=ts.value)
+
+
+def env3d_adjacency(p, p_state, p_active, e_state):
+    ps, pa, es = _c(p_state, np.float64), _c(p_active, np.uint8), _c(e_state, np.float64)
+    pp = np.zeros((p.N, p.N), np.uint8)
+    pe = np.zeros(p.N, np.uint8)
+    lib().orc_env3d_adjacency(C.byref(p), _p(ps), _p(pa), _p(es), _p(pp), _p(pe))
+    return pp, pe
+
+
+def env3d_iteration(p, st):
+    """Batched adjacency -> evader move -> step over st's contiguous arrays (mutated in place)."""
+    B = st["p_state"].shape[0]
+    lib().orc_env3d_iteration(C.byref(p), C.c_int32(B), _p(st["p_state"]), _p(st["p_active"]), _p(st["e_state"]),
+                              _p(st["e_active"]), _p(st["target"]), _p(st["action"]), _p(st["e_action"]),
+                              _p(st["time_step"]), _p(st["reward"]), _p(st["done"]), _p(st["pp_adj"]), _p(st["pe_adj"]))
