@@ -108,6 +108,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def policy_flops_per_agent(N, O, D, head=2304):
+    """forward FLOPs per agent per network (mult-add = 2)."""
+    return 2048 * N + 1024 + 1024 * O + 256 * (N + 1 + O) + 3 * 32768 + 99328 + D * (256 * N + 98304) + 393216 + head
+
+
+def measured_tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1500.0)))
+    return 1500.0
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -308,8 +322,8 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------ our arm
 class PolicyEpisodeGraph:
     """MAPPO.run_episode for all envs (network in the loop) captured as ONE CUDA graph: per env step
-    observe -> actor encoder -> critic encoder -> GRU cells -> heads (sample, log-prob, value) -> A* replan when due ->
-    fused evader-move/step/reward-norm/store kernel; ~70 kernels per step, no host involvement on replay."""
+    observe -> fused policy step (encoder + GRU + heads of both networks, ONE launch) -> A* replan when due ->
+    fused evader-move/step/reward-norm/store kernel; 3-4 kernels per step, no host involvement on replay."""
 
     def __init__(self, torch, mappo, env, arena, T, seed):
         from distributed_multi_agent_reinforcement_learning_b200 import _lib
@@ -455,30 +469,34 @@ def run_ours(args):
              "minibatches": -(-B // mappo.mini_batch_size), "dtype": "f32 (TF32 off)",
              "allreduce": "1 x SUM over the flat gradient arena (%d floats)" % mappo.ac_optimizer.flat_grad.numel()}
 
-    # ---- per-kernel durations of the env kernels: CUDA events around every launch of one eager env-only episode ----
+    # ---- per-kernel durations: CUDA events around every launch of ONE eager network-in-the-loop episode (same stream) -----
     env.restore(snap)
     timers = {}
-    env.rollout_closed(arena, T, 0, seed=0xB200 + rank, timers=timers)
+    mappo.rollout_batched(env, arena, T, seed=0xB200 + rank, timers=timers)
     torch.cuda.synchronize()
     kernel_table = {k: {"launches": len(v), "total_ms": sum(a.elapsed_time(b) for a, b in v)} for k, v in timers.items()}
     for v in kernel_table.values():
         v["avg_us"] = 1e3 * v["total_ms"] / v["launches"]
     env.restore(snap)
     ms_episode = ms_total / args.steps
-    peak, peak_src = measured_peaks()
-    rk = kernel_table["rollout_kernel(closed)"]
-    steps_per_launch = T / rk["launches"]
-    alg_bytes = SURVEY_BYTES_PER_AGENT_STEP * B * N * steps_per_launch
-    achieved = alg_bytes / (rk["avg_us"] * 1e-6) / 1e9
-    roofline = {"kernel": "rollout_kernel<8,1,closed> (observe + evader move + step + reward-norm + store, %d env steps per launch)" % steps_per_launch,
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": 8.66e6, "traffic_source": "profiles/r1_rollout_kernel_ncu_raw.csv (dram read+write per 10-step launch)",
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": rk["avg_us"],
-                "share_of_env_only_episode": rk["total_ms"] / env_ms, "share_of_step": rk["total_ms"] / ms_episode,
-                "note": "118 B/agent-step (SURVEY 8d) x 32768 agents x 10 steps per launch.  One launch's working set (38 MB) "
-                        "lives in the 126 MB L2 and the kernel issues ~2400 warp-instructions per warp-step (exact fp64 RK4 "
-                        "with true divisions), so at 4096 envs it is issue/latency-bound, not HBM-bound; with the networks in "
-                        "the loop the step is dominated by the policy kernels and GEMMs"}
+    hbm_peak, peak_src = measured_peaks()
+    tensor_peak = measured_tensor_peak()
+    pk = kernel_table["policy_step_kernel"]
+    flops_launch = 2 * policy_flops_per_agent(N, env.O, cfg.algo.depth) * B * N        # actor + critic
+    achieved = flops_launch / (pk["avg_us"] * 1e-6) / 1e12
+    # HBM traffic the fused kernel needs per launch: state/adjacency in, history in, embedding + hidden (r/w) + heads out
+    bytes_launch = B * N * (32 + 4 + 1 + 24 + 2 * (cfg.algo.depth * 512 + 512 + 4 * 512) + 12)
+    roofline = {"kernel": "policy_step_kernel (DHGN encoder + 2-layer GRU + heads of actor AND critic, one launch per env step; "
+                          "tcgen05 kind::tf32, 3xTF32 split for fp32-level accuracy, accumulators in TMEM)",
+                "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16; kind::tf32 runs at half of it "
+                                                "and the 3xTF32 split issues 3 MMAs per product, so this kernel's ceiling is frac = 1/6)",
+                "algorithmic_flops_per_launch": flops_launch, "flops_per_agent_per_network": policy_flops_per_agent(N, env.O, cfg.algo.depth),
+                "avg_launch_us": pk["avg_us"], "share_of_step": pk["total_ms"] / ms_episode,
+                "hbm_bytes_per_launch_algorithmic": bytes_launch,
+                "hbm_GBps_at_this_duration": bytes_launch / (pk["avg_us"] * 1e-6) / 1e9, "hbm_peak_GBps": hbm_peak,
+                "note": "SURVEY 8(d) FLOP count per agent and network (obstacle messages counted for all O slots: upper bound) x "
+                        "B*N rows x 2 networks per launch"}
 
     if rank == 0:
         # ---- CPU baseline: oracle port (C env + torch-CPU network restatement) on the host cores, bounded sample ----
@@ -489,7 +507,7 @@ def run_ours(args):
             "dtype": "f64 env / f32 networks", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": pol.our_launches * args.steps, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "env_only": env_only, "train": train, "kernel_ms_per_env_only_episode": kernel_table}))
+            "cpu_baseline": cpu, "env_only": env_only, "train": train, "kernel_ms_per_episode": kernel_table}))
     if world > 1:
         dist.destroy_process_group()
 

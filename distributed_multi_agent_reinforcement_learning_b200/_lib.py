@@ -80,6 +80,12 @@ _PROTOTYPES = {
     "marl_ppo_head": (C.c_int, [_I64, _I32, _I32] + [_VP] * 12 + [_F32, _F32] + [_VP] * 7),
     "marl_act_head": (C.c_int, [_I64, _I32, _I32] + [_VP] * 6 + [_U64, _I32, _I32] + [_VP] * 5),
     "marl_gemm_tf32x3": (C.c_int, [_I32, _I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _I64, _I32, _VP]),
+    "marl_policy_pack_bytes": (_I64, [_I32, _I32]),
+    "marl_policy_pack": (C.c_int, [_VP, _I32, _I32, _I32, _VP, _VP]),
+    "marl_policy_rollout_step": (C.c_int, [_VP] * 6),
+    "marl_policy_pack_bytes": (_I64, [_I32, _I32]),
+    "marl_policy_pack": (C.c_int, [_VP, _I32, _I32, _I32, _VP, _VP]),
+    "marl_policy_rollout_step": (C.c_int, [_VP] * 6),
     "marl_clip_workspace_bytes": (_I64, [_I64]),
     "marl_clip_grad_norm": (C.c_int, [_I64, _VP, _F32, _VP, _VP, _VP]),
     "marl_adam_step": (C.c_int, [_I64, _VP, _VP, _VP, _VP, _F32, _F32, _F32, _F32, _I64, _VP]),

@@ -1,0 +1,1081 @@
+// policy_fused.cu — ONE kernel for a whole rollout step of the DHGN actor / critic (DHGN/mappo_parallel.py:116-545 as used by
+// MAPPO.run_episode :758-801): message passing + mean aggregation of the three relations, AGG_vertex, semantic layer, FCRA
+// blocks, 2-layer GRU cell and the heads (softmax / sample / log-prob, value) for a tile of 128 (env, agent) rows, with every
+// activation staying on chip.  HBM traffic per row is only what the step really needs: the env state / packed adjacency in,
+// the history embeddings in, the new embedding, hidden states and action / log-prob / value out.
+//
+// Tensor cores: every 128-wide dense layer is a chain of "units" (one unit = [128 rows x K=128] x [K=128 x n_out]) issued as
+// tcgen05.mma.kind::tf32 with fp32 accumulation in TMEM.  fp32-level accuracy comes from the 3xTF32 split
+// (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, see gemm_tf32x3.cu); the weights are pre-split and pre-swizzled once per rollout
+// (marl_policy_pack) into the exact shared-memory image of each k-block, so that the producer is a single elected thread
+// issuing cp.async.bulk copies (32 KB per stage) that complete on an mbarrier.
+//
+// CTA = one (row tile, network) work item, 10 warps:
+//   warps 0-7  workers: SIMT phases (messages, FCRA neighbour mean, hidden-state load) that write the activation tile X
+//              straight into the canonical K-major SWIZZLE_128B operand layout (hi and lo planes), and the epilogues
+//              (tcgen05.ld -> bias / ReLU / GRU cell / heads -> X again, plus the few global stores);
+//   warp 8     weight loader (elected lane): streams the packed units through a 3-stage ring;
+//   warp 9     MMA issuer (elected lane) + TMEM allocation (all 512 columns: the GRU needs four 128-column accumulators).
+// Workers and the issuer follow the same static unit program and hand the tile back and forth with two mbarriers
+// (a_ready: 256 arrivals, mma_done: tcgen05.commit).
+// Shared memory: X 128 KB (4 k-blocks x (hi 16 KB + lo 16 KB)) + 3 x 32 KB weight stages.
+#include "common.cuh"
+
+namespace marl {
+namespace pf {
+
+constexpr int ROWS = 128, E = 128, NSTAGE = 3, MAXD = 3, MAX_UNITS = 40;
+constexpr int BAR_A_READY = 2 * NSTAGE, BAR_MMA_DONE = 2 * NSTAGE + 1;
+constexpr int TILE = ROWS * 128;          // 16 KB: 128 rows x 128 B (one k-block of 32 floats)
+constexpr int XKB = 2 * TILE;             // one k-block of X: hi plane + lo plane
+constexpr int X_BYTES = 4 * XKB;          // K = 128
+constexpr int WSTAGE = 2 * TILE;          // one k-block of a 128-row weight unit: hi + lo
+constexpr int SMEM_BYTES = X_BYTES + NSTAGE * WSTAGE + 3072 /*barriers, fp32 state of the tile*/;   // 232 448 B = 227 KB
+constexpr int WORKERS = 256, THREADS = 320;
+
+struct Unit {
+    uint32_t off;        // byte offset of the packed unit
+    uint16_t n_out;      // 128 or 16
+    uint16_t acc_col;    // TMEM column of the accumulator
+    uint8_t accumulate;  // add to what the accumulator holds
+    uint8_t last;        // last unit of its group (the workers take over afterwards)
+    uint16_t pad;
+};
+
+struct NetArgs {
+    const unsigned char *packed;
+    int n_units;
+    Unit u[MAX_UNITS];
+    const float *msg_w[3], *msg_b[3];
+    const float *b_av, *sem_w, *b_sem;
+    int sem_ld;
+    const float *b_aggf[MAXD], *b_f[MAXD];
+    const float *b_ih[2], *b_hh[2];
+    const float *head_b;
+    const float *head_w_eff;   // critic: effective [E] row (fp32); actor: unused
+    const float *hist[MAXD];   // [B,N,E] history embeddings, k = 0 most recent; null = zeros
+    float *emb_out;            // [B,N,E]
+    float *hidden;             // [2, R, E] in/out
+    int all_ones;              // critic
+};
+
+struct StepArgs {
+    int B, N, O, NW, OW, depth, rows_per_tile, n_tiles, A;
+    int64_t R;
+    const double *p_state, *e_state;
+    const int32_t *oxy, *map_id, *o_count;
+    const uint32_t *p_adj;
+    const uint8_t *e_adj;
+    const uint32_t *o_adj;
+    int32_t *action;
+    float *logp, *value;
+    uint64_t seed;
+    int t, deterministic, force_action, net_first, net_count;
+    long long *dbg;   // optional [grid,16] per-CTA phase cycle counters (profiling aid)
+    NetArgs net[2];   // 0 actor, 1 critic
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// K-major SWIZZLE_128B canonical layout (rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t idesc_tf32(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+#define PF_TMEM_LD32(dst, addr)                                                                                         \
+    asm volatile(                                                                                                       \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                       \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                       \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                       \
+        : "=r"(dst[0]), "=r"(dst[1]), "=r"(dst[2]), "=r"(dst[3]), "=r"(dst[4]), "=r"(dst[5]), "=r"(dst[6]), "=r"(dst[7]),   \
+          "=r"(dst[8]), "=r"(dst[9]), "=r"(dst[10]), "=r"(dst[11]), "=r"(dst[12]), "=r"(dst[13]), "=r"(dst[14]),            \
+          "=r"(dst[15]), "=r"(dst[16]), "=r"(dst[17]), "=r"(dst[18]), "=r"(dst[19]), "=r"(dst[20]), "=r"(dst[21]),          \
+          "=r"(dst[22]), "=r"(dst[23]), "=r"(dst[24]), "=r"(dst[25]), "=r"(dst[26]), "=r"(dst[27]), "=r"(dst[28]),          \
+          "=r"(dst[29]), "=r"(dst[30]), "=r"(dst[31])                                                                      \
+        : "r"(addr))
+#define PF_TMEM_LD16(dst, addr)                                                                                         \
+    asm volatile(                                                                                                       \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                                       \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                                \
+        : "=r"(dst[0]), "=r"(dst[1]), "=r"(dst[2]), "=r"(dst[3]), "=r"(dst[4]), "=r"(dst[5]), "=r"(dst[6]), "=r"(dst[7]),   \
+          "=r"(dst[8]), "=r"(dst[9]), "=r"(dst[10]), "=r"(dst[11]), "=r"(dst[12]), "=r"(dst[13]), "=r"(dst[14]),            \
+          "=r"(dst[15])                                                                                                    \
+        : "r"(addr))
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// hi = a rounded to TF32 precision with the discarded bits cleared; lo = a - hi EXACTLY (all 23 mantissa bits kept, the
+// tensor core reads its top 10): hi + lo == a, so an activation can be read back from X at full fp32 precision.
+__device__ __forceinline__ void split_tf32(float a, float &hi, float &lo)
+{
+    const uint32_t u = __float_as_uint(a);
+    hi = __uint_as_float((u + 0x1000u) & 0xFFFFE000u);
+    lo = a - hi;
+}
+__device__ __forceinline__ int x_off(int row, int c4) { return (c4 >> 3) * XKB + row * 128 + (((c4 & 7) ^ (row & 7)) << 4); }
+// element group (row, channels 4*c4 .. 4*c4+3) of the activation tile, both planes
+__device__ __forceinline__ void x_store4(unsigned char *X, int row, int c4, float4 v)
+{
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x);
+    split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z);
+    split_tf32(v.w, h.w, l.w);
+    const int off = x_off(row, c4);
+    *reinterpret_cast<float4 *>(X + off) = h;
+    *reinterpret_cast<float4 *>(X + off + TILE) = l;
+}
+__device__ __forceinline__ float4 x_load4(const unsigned char *X, int row, int c4)
+{
+    const int off = x_off(row, c4);
+    const float4 h = *reinterpret_cast<const float4 *>(X + off), l = *reinterpret_cast<const float4 *>(X + off + TILE);
+    return make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+}
+
+struct Ctx {
+    const StepArgs *a;
+    const NetArgs *na;
+    unsigned char *X;
+    int64_t row0;        // first global row of the tile
+    int warp, lane;
+    uint32_t tmem, bar_a_ready, bar_mma_done;
+    int group;           // groups completed so far (parity of mma_done)
+    float4 *s_p;         // [128] fp32 pursuer state of the tile's rows (converted once)
+    float4 *s_e;         // [32] fp32 evader state of the tile's envs (when the tile has <= 32 envs)
+    float *s_val;        // [2][128] scratch for the critic value (aliases s_p, which is dead by then)
+};
+
+__device__ __forceinline__ bool row_info(const Ctx &c, int r, int64_t &gr, int &env, int &i)
+{
+    gr = c.row0 + r;
+    const bool ok = r < c.a->rows_per_tile && gr < c.a->R;
+    env = ok ? (int)(gr / c.a->N) : 0;
+    i = ok ? (int)(gr - (int64_t)env * c.a->N) : 0;
+    return ok;
+}
+__device__ __forceinline__ float4 load_p(const StepArgs *a, int64_t gr)
+{
+    const double2 *q = reinterpret_cast<const double2 *>(a->p_state + gr * 4);
+    const double2 u = q[0], v = q[1];
+    return make_float4((float)u.x, (float)u.y, (float)v.x, (float)v.y);
+}
+__device__ __forceinline__ float4 load_e(const StepArgs *a, int env)
+{
+    const double2 *q = reinterpret_cast<const double2 *>(a->e_state + (int64_t)env * 4);
+    const double2 u = q[0], v = q[1];
+    return make_float4((float)u.x, (float)u.y, (float)v.x, (float)v.y);
+}
+__device__ __forceinline__ float4 e_of(const Ctx &c, int r, int env)
+{
+    return (ROWS / c.a->N <= 32) ? c.s_e[r / c.a->N] : load_e(c.a, env);
+}
+__device__ __forceinline__ float dot4w(const float (&w)[4], float a0, float a1, float a2, float a3, float b)
+{
+    return fmaf(w[3], a3, fmaf(w[2], a2, fmaf(w[1], a1, fmaf(w[0], a0, 0.f)))) + b;
+}
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// workers: hand X to the issuer, then wait until the group's MMAs have completed
+__device__ __forceinline__ void hand_over(Ctx &c)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    mbar_arrive(c.bar_a_ready);
+    mbar_wait(c.bar_mma_done, (uint32_t)(c.group & 1));
+    tc_fence_after();
+    ++c.group;
+}
+
+// per-lane slices (channels 4*lane .. 4*lane+3) of one MSG layer, vector loads
+__device__ __forceinline__ void load_msg_weights(const NetArgs *na, int rel, int lane, float (&w)[4][8], float (&b)[4])
+{
+    const float *W = na->msg_w[rel];
+    const float4 bb = __ldg(reinterpret_cast<const float4 *>(na->msg_b[rel]) + lane);
+    b[0] = bb.x; b[1] = bb.y; b[2] = bb.z; b[3] = bb.w;
+    if (rel == 0) {
+        const float4 *Wv = reinterpret_cast<const float4 *>(W) + 8 * lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 lo = __ldg(Wv + 2 * q), hi = __ldg(Wv + 2 * q + 1);
+            w[q][0] = lo.x; w[q][1] = lo.y; w[q][2] = lo.z; w[q][3] = lo.w;
+            w[q][4] = hi.x; w[q][5] = hi.y; w[q][6] = hi.z; w[q][7] = hi.w;
+        }
+    } else {
+        const float4 *Wv = reinterpret_cast<const float4 *>(W) + 4 * lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 lo = __ldg(Wv + q);
+            w[q][0] = lo.x; w[q][1] = lo.y; w[q][2] = lo.z; w[q][3] = lo.w;
+            w[q][4] = w[q][5] = w[q][6] = w[q][7] = 0.f;
+        }
+    }
+}
+
+// ---- DHGN.message + mean aggregation, generic per-row path (any N) -> X ----------------------------------------------------
+// Same arithmetic as msg_agg_fwd_kernel (policy_kernels.cu).  lane l owns channels 4l..4l+3.
+__device__ void phase_msg_generic(const Ctx &c, int rel)
+{
+    const StepArgs *a = c.a;
+    const NetArgs *na = c.na;
+    const int lane = c.lane, N = a->N;
+    float w[4][8], b[4];
+    load_msg_weights(na, rel, lane, w, b);
+#pragma unroll 1
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = 16 * c.warp + rr;
+        int64_t gr;
+        int env, i;
+        const bool ok = row_info(c, r, gr, env, i);
+        float out[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ok) {
+            const float4 pi = c.s_p[r], ev = e_of(c, r, env);
+            const float dex = pi.x - ev.x, dey = pi.y - ev.y, dez = pi.z - ev.z, dew = pi.w - ev.w;
+            if (rel == 0) {
+                int cnt = 0;
+                for (int j = 0; j < N; ++j) {
+                    const bool on = na->all_ones || ((a->p_adj[gr * a->NW + (j >> 5)] >> (j & 31)) & 1u);
+                    if (!on) continue;
+                    ++cnt;
+                    const float4 pj = c.s_p[r - i + j];
+                    const float d0 = pi.x - pj.x, d1 = pi.y - pj.y, d2 = pi.z - pj.z, d3 = pi.w - pj.w;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float v = fmaf(w[q][3], d3, fmaf(w[q][2], d2, fmaf(w[q][1], d1, fmaf(w[q][0], d0, 0.f))));
+                        v = fmaf(w[q][7], dew, fmaf(w[q][6], dez, fmaf(w[q][5], dey, fmaf(w[q][4], dex, v)))) + b[q];
+                        out[q] += fmaxf(v, 0.f);
+                    }
+                }
+                const float nrm = cnt ? 1.f / fmaxf((float)cnt, 1e-12f) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) out[q] *= nrm;
+            } else if (rel == 1) {
+                const float e_on = na->all_ones ? 1.f : (float)a->e_adj[gr];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    out[q] = e_on * fmaxf(dot4w(reinterpret_cast<const float(&)[4]>(w[q]), dex, dey, dez, dew, b[q]), 0.f);
+            } else {
+                const int m = a->map_id ? a->map_id[env] : env;
+                const int2 *oxy = reinterpret_cast<const int2 *>(a->oxy) + (int64_t)m * a->O;
+                int cnt = 0;
+                if (na->all_ones) {
+                    cnt = a->o_count[m];
+                    for (int k = 0; k < cnt; ++k) {
+                        const int2 o = __ldg(oxy + k);
+                        const float d0 = pi.x - (float)o.x, d1 = pi.y - (float)o.y;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            out[q] += fmaxf(dot4w(reinterpret_cast<const float(&)[4]>(w[q]), d0, d1, pi.z, pi.w, b[q]), 0.f);
+                    }
+                } else {
+                    for (int wd = 0; wd < a->OW; ++wd) {
+                        uint32_t bits = a->o_adj[gr * a->OW + wd];
+                        cnt += __popc(bits);
+                        while (bits) {
+                            const int k = wd * 32 + __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const int2 o = __ldg(oxy + k);
+                            const float d0 = pi.x - (float)o.x, d1 = pi.y - (float)o.y;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                out[q] += fmaxf(dot4w(reinterpret_cast<const float(&)[4]>(w[q]), d0, d1, pi.z, pi.w, b[q]), 0.f);
+                        }
+                    }
+                }
+                const float nrm = cnt ? 1.f / fmaxf((float)cnt, 1e-12f) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) out[q] *= nrm;
+            }
+        }
+        x_store4(c.X, r, lane, make_float4(out[0], out[1], out[2], out[3]));
+    }
+}
+
+// ---- DHGN.message + mean aggregation, env-grouped path for N = NA in {4, 8, 16} (16 % NA == 0, O <= 256) -> X ---------------
+// A warp owns 16/NA whole envs.  Everything shared by the rows of an env is computed once per env and kept in registers:
+//   relation 0: relu(W0[:, :4](p_i - p_j) + W0[:, 4:](p_i - e) + b0) = relu(a_i - q_j),  q_j = W0[:, :4] p_j,
+//               a_i = q_i + W0[:, 4:](p_i - e) + b0                       (3 instructions per (i, j, channel));
+//   relation 2, critic (all cells of the map): sum_k relu(cc_i - u_k) = ((n cc_i - sum_k u_k) + sum_k |cc_i - u_k|) / 2 with
+//               cc_i = W2 p_i + b2, u_k = W2[:, :2] o_k                    (2 instructions per (i, k, channel));
+//   the map's boundary cells live in registers (lane l holds cells l, l+32, ...) and are broadcast with shuffles.
+template <int NA>
+__device__ void phase_msg_fast(const Ctx &c, int rel)
+{
+    const StepArgs *a = c.a;
+    const NetArgs *na = c.na;
+    const int lane = c.lane;
+    float w[4][8], b[4];
+    load_msg_weights(na, rel, lane, w, b);
+    constexpr int RC = NA < 8 ? NA : 8;      // rows per register chunk of the critic's obstacle relation
+#pragma unroll 1
+    for (int g = 0; g < 16 / NA; ++g) {
+        const int r0 = 16 * c.warp + g * NA;
+        int64_t gr0;
+        int env, i0;
+        const bool ok = row_info(c, r0, gr0, env, i0);     // rows of an env are valid together
+        if (!ok) {
+#pragma unroll
+            for (int i = 0; i < NA; ++i) x_store4(c.X, r0 + i, lane, make_float4(0.f, 0.f, 0.f, 0.f));
+            continue;
+        }
+        const float4 ev = c.s_e[r0 / NA];
+        if (rel == 0) {
+            float qj[NA][4];
+            float4 pj[NA];
+#pragma unroll
+            for (int j = 0; j < NA; ++j) {
+                pj[j] = c.s_p[r0 + j];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) qj[j][q] = fmaf(w[q][3], pj[j].w, fmaf(w[q][2], pj[j].z, fmaf(w[q][1], pj[j].y, w[q][0] * pj[j].x)));
+            }
+#pragma unroll
+            const uint32_t my_word = (!na->all_ones && lane < NA) ? a->p_adj[(gr0 + lane) * a->NW] : 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                const uint32_t word = __shfl_sync(0xffffffffu, my_word, i);
+                const int cnt = __popc(word & ((NA == 32) ? 0xffffffffu : ((1u << NA) - 1u)));
+                const float dex = pj[i].x - ev.x, dey = pj[i].y - ev.y, dez = pj[i].z - ev.z, dew = pj[i].w - ev.w;
+                float ai[4], acc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    ai[q] = (qj[i][q] + fmaf(w[q][7], dew, fmaf(w[q][6], dez, fmaf(w[q][5], dey, w[q][4] * dex)))) + b[q];
+                    acc[q] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < NA; ++j) {
+                    const bool on = (word >> j) & 1u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float t = fmaxf(ai[q] - qj[j][q], 0.f);
+                        acc[q] += on ? t : 0.f;
+                    }
+                }
+                const float nrm = cnt ? 1.f / fmaxf((float)cnt, 1e-12f) : 0.f;
+                x_store4(c.X, r0 + i, lane, make_float4(acc[0] * nrm, acc[1] * nrm, acc[2] * nrm, acc[3] * nrm));
+            }
+        } else if (rel == 1) {
+            const float my_on = (!na->all_ones && lane < NA) ? (float)a->e_adj[gr0 + lane] : 1.f;
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                const float4 pi = c.s_p[r0 + i];
+                const float e_on = __shfl_sync(0xffffffffu, my_on, i);
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    o[q] = e_on * fmaxf(dot4w(reinterpret_cast<const float(&)[4]>(w[q]), pi.x - ev.x, pi.y - ev.y, pi.z - ev.z, pi.w - ev.w, b[q]), 0.f);
+                x_store4(c.X, r0 + i, lane, make_float4(o[0], o[1], o[2], o[3]));
+            }
+        } else {
+            const int m = a->map_id ? a->map_id[env] : env;
+            const int2 *oxy = reinterpret_cast<const int2 *>(a->oxy) + (int64_t)m * a->O;
+            float2 my_o[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                my_o[t] = make_float2(0.f, 0.f);
+                const int k = lane + 32 * t;
+                if (t < a->OW && k < a->O) { const int2 o = __ldg(oxy + k); my_o[t] = make_float2((float)o.x, (float)o.y); }
+            }
+            if (na->all_ones) {
+                const int n = a->o_count[m];
+                float sx = 0.f, sy = 0.f;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) if (lane + 32 * t < n) { sx += my_o[t].x; sy += my_o[t].y; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+                const float nrm = n ? 1.f / fmaxf((float)n, 1e-12f) : 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < NA / RC; ++ch) {
+                    float cc[RC][4], acc[RC][4];
+#pragma unroll
+                    for (int rr = 0; rr < RC; ++rr) {
+                        const float4 p = c.s_p[r0 + ch * RC + rr];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { cc[rr][q] = dot4w(reinterpret_cast<const float(&)[4]>(w[q]), p.x, p.y, p.z, p.w, b[q]); acc[rr][q] = 0.f; }
+                    }
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int kn = min(32, n - 32 * t);        // warp-uniform
+                        for (int kk = 0; kk < kn; ++kk) {
+                            const float ox = __shfl_sync(0xffffffffu, my_o[t].x, kk), oy = __shfl_sync(0xffffffffu, my_o[t].y, kk);
+                            float u[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) u[q] = fmaf(w[q][1], oy, w[q][0] * ox);
+#pragma unroll
+                            for (int rr = 0; rr < RC; ++rr)
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) acc[rr][q] += fabsf(cc[rr][q] - u[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < RC; ++rr) {
+                        float o[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float su = fmaf(w[q][1], sy, w[q][0] * sx);          // sum_k u_k
+                            o[q] = fmaxf(0.5f * (((float)n * cc[rr][q] - su) + acc[rr][q]), 0.f) * nrm;
+                        }
+                        x_store4(c.X, r0 + ch * RC + rr, lane, make_float4(o[0], o[1], o[2], o[3]));
+                    }
+                }
+            } else {
+                // this warp's 16 rows x OW adjacency words: lane l holds word l of the group's flattened [NA][OW] block(s)
+                uint32_t my_bits[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int idx = lane + 32 * t;
+                    my_bits[t] = idx < NA * a->OW ? a->o_adj[gr0 * a->OW + idx] : 0u;
+                }
+#pragma unroll 1
+                for (int i = 0; i < NA; ++i) {
+                    const float4 pi = c.s_p[r0 + i];
+                    float cc[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cc[q] = dot4w(reinterpret_cast<const float(&)[4]>(w[q]), pi.x, pi.y, pi.z, pi.w, b[q]);
+                    int cnt = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int idx = i * a->OW + t;
+                        uint32_t bits = 0u;
+                        if (t < a->OW) {
+                            const uint32_t v0 = __shfl_sync(0xffffffffu, my_bits[0], idx & 31), v1 = __shfl_sync(0xffffffffu, my_bits[1], idx & 31);
+                            const uint32_t v2 = __shfl_sync(0xffffffffu, my_bits[2], idx & 31), v3 = __shfl_sync(0xffffffffu, my_bits[3], idx & 31);
+                            bits = (idx >> 5) == 0 ? v0 : ((idx >> 5) == 1 ? v1 : ((idx >> 5) == 2 ? v2 : v3));
+                        }
+                        cnt += __popc(bits);
+                        while (bits) {                                                    // warp-uniform
+                            const int kk = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const float ox = __shfl_sync(0xffffffffu, my_o[t].x, kk), oy = __shfl_sync(0xffffffffu, my_o[t].y, kk);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) acc[q] += fmaxf(cc[q] - fmaf(w[q][1], oy, w[q][0] * ox), 0.f);
+                        }
+                    }
+                    const float nrm = cnt ? 1.f / fmaxf((float)cnt, 1e-12f) : 0.f;
+                    x_store4(c.X, r0 + i, lane, make_float4(acc[0] * nrm, acc[1] * nrm, acc[2] * nrm, acc[3] * nrm));
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ bool fast_env_path(const StepArgs *a) { return (a->N == 4 || a->N == 8 || a->N == 16) && a->OW <= 8; }
+
+__device__ void phase_msg(const Ctx &c, int rel)
+{
+    if (!fast_env_path(c.a)) phase_msg_generic(c, rel);
+    else if (c.a->N == 8) phase_msg_fast<8>(c, rel);
+    else if (c.a->N == 16) phase_msg_fast<16>(c, rel);
+    else phase_msg_fast<4>(c, rel);
+}
+
+// ---- DHGN.fcra neighbour mean of the k-th history embedding -> X --------------------------------------------------------
+__device__ void phase_fcra_generic(const Ctx &c, int k)
+{
+    const StepArgs *a = c.a;
+    const NetArgs *na = c.na;
+    const float *hist = na->hist[k];
+    const int N = a->N;
+#pragma unroll 1
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = 16 * c.warp + rr;
+        int64_t gr;
+        int env, i;
+        const bool ok = row_info(c, r, gr, env, i);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && hist) {
+            int cnt = 0;
+            for (int j = 0; j < N; ++j) {
+                const bool on = na->all_ones || ((a->p_adj[gr * a->NW + (j >> 5)] >> (j & 31)) & 1u);
+                if (!on) continue;
+                ++cnt;
+                const float4 h = __ldg(reinterpret_cast<const float4 *>(hist + ((int64_t)env * N + j) * E) + c.lane);
+                acc.x += h.x; acc.y += h.y; acc.z += h.z; acc.w += h.w;
+            }
+            const float nrm = cnt ? 1.f / fmaxf((float)cnt, 1e-12f) : 0.f;
+            acc.x *= nrm; acc.y *= nrm; acc.z *= nrm; acc.w *= nrm;
+        }
+        x_store4(c.X, r, c.lane, acc);
+    }
+}
+
+template <int NA>
+__device__ void phase_fcra_fast(const Ctx &c, int k)
+{
+    const StepArgs *a = c.a;
+    const NetArgs *na = c.na;
+    const float *hist = na->hist[k];
+#pragma unroll 1
+    for (int g = 0; g < 16 / NA; ++g) {
+        const int r0 = 16 * c.warp + g * NA;
+        int64_t gr0;
+        int env, i0;
+        const bool ok = row_info(c, r0, gr0, env, i0);
+        const uint32_t my_word = !ok ? 0u : ((!na->all_ones && c.lane < NA) ? a->p_adj[(gr0 + c.lane) * a->NW] : ((1u << NA) - 1u));
+        float4 h[NA];
+#pragma unroll
+        for (int j = 0; j < NA; ++j)       // all of the env's history rows first: NA independent 512-byte warp loads in flight
+            h[j] = (ok && hist) ? __ldg(reinterpret_cast<const float4 *>(hist + (gr0 + j) * E) + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const uint32_t word = __shfl_sync(0xffffffffu, my_word, i);
+            const int cnt = __popc(word & ((1u << NA) - 1u));
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < NA; ++j) {
+                const bool on = (word >> j) & 1u;
+                acc.x += on ? h[j].x : 0.f; acc.y += on ? h[j].y : 0.f; acc.z += on ? h[j].z : 0.f; acc.w += on ? h[j].w : 0.f;
+            }
+            const float nrm = cnt ? 1.f / fmaxf((float)cnt, 1e-12f) : 0.f;
+            x_store4(c.X, r0 + i, c.lane, make_float4(acc.x * nrm, acc.y * nrm, acc.z * nrm, acc.w * nrm));
+        }
+    }
+}
+
+__device__ void phase_fcra(const Ctx &c, int k)
+{
+    if (!fast_env_path(c.a)) phase_fcra_generic(c, k);
+    else if (c.a->N == 8) phase_fcra_fast<8>(c, k);
+    else if (c.a->N == 16) phase_fcra_fast<16>(c, k);
+    else phase_fcra_fast<4>(c, k);
+}
+
+// ---- previous hidden state of GRU layer l -> X (16 independent 512-byte warp loads in flight) ----------------------------
+__device__ void phase_load_hidden(const Ctx &c, int l)
+{
+    const float *h = c.na->hidden + (int64_t)l * c.a->R * E;
+    float4 v[16];
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+        int64_t gr;
+        int env, i;
+        const bool ok = row_info(c, 16 * c.warp + rr, gr, env, i);
+        v[rr] = ok ? *(reinterpret_cast<const float4 *>(h + gr * E) + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) x_store4(c.X, 16 * c.warp + rr, c.lane, v[rr]);
+}
+
+// X (exact fp32 = hi + lo) -> global rows, coalesced: warp w copies rows 16w..16w+15, 512 bytes per row
+__device__ void copy_out(const Ctx &c, float *g)
+{
+#pragma unroll 4
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = 16 * c.warp + rr;
+        int64_t gr;
+        int env, i;
+        if (row_info(c, r, gr, env, i)) *(reinterpret_cast<float4 *>(g + gr * E) + c.lane) = x_load4(c.X, r, c.lane);
+    }
+}
+
+// ---- epilogue: X <- act(acc + bias [+ W_p p_i]) ; optional global copy ---------------------------------------------------
+// thread <-> row 32*(warp&3)+lane (its TMEM lane), columns [64*(warp>>2), +64)
+__device__ void epi_store(const Ctx &c, int acc_col, const float *bias, bool relu, const float *wp, int wp_ld, float *gout)
+{
+    const int row = 32 * (c.warp & 3) + c.lane, hh = c.warp >> 2;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wp) p = c.s_p[row];
+    const uint32_t taddr = c.tmem + ((uint32_t)(32 * (c.warp & 3)) << 16) + (uint32_t)acc_col;
+#pragma unroll 1
+    for (int c0 = 64 * hh; c0 < 64 * hh + 64; c0 += 32) {
+        uint32_t v[32];
+        PF_TMEM_LD32(v, taddr + (uint32_t)c0);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const int col = c0 + j;
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
+            float4 o = make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y, __uint_as_float(v[j + 2]) + bb.z,
+                                   __uint_as_float(v[j + 3]) + bb.w);
+            if (wp) {
+                float *of = reinterpret_cast<float *>(&o);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = __ldg(reinterpret_cast<const float4 *>(wp + (int64_t)(col + q) * wp_ld));
+                    of[q] += fmaf(wv.w, p.w, fmaf(wv.z, p.z, fmaf(wv.y, p.y, fmaf(wv.x, p.x, 0.f))));
+                }
+            }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            x_store4(c.X, row, col >> 2, o);
+        }
+    }
+    if (gout) {
+        worker_sync();
+        copy_out(c, gout);
+    }
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+// ---- epilogue: GRU cell of layer l (torch gate order r, z, n); h' -> X (then coalesced to global); critic layer 1: value ---
+// h_prev is read back from X (it is the A operand of the W_hh group, exact fp32).  The gates use ex2-based exp and the fast
+// division (abs error ~1e-7, inside the 1e-5 forward tolerance).
+__device__ void epi_cell(const Ctx &c, int l, bool want_value)
+{
+    const NetArgs *na = c.na;
+    const int row = 32 * (c.warp & 3) + c.lane, hh = c.warp >> 2;
+    const float *bi = na->b_ih[l], *bh = na->b_hh[l];
+    const uint32_t taddr = c.tmem + ((uint32_t)(32 * (c.warp & 3)) << 16);
+    float vdot = 0.f;
+#pragma unroll 1
+    for (int c0 = 64 * hh; c0 < 64 * hh + 64; c0 += 16) {
+        uint32_t ar[16], az[16], an[16], ahn[16];
+        PF_TMEM_LD16(ar, taddr + (uint32_t)c0);
+        PF_TMEM_LD16(az, taddr + (uint32_t)(128 + c0));
+        PF_TMEM_LD16(an, taddr + (uint32_t)(256 + c0));
+        PF_TMEM_LD16(ahn, taddr + (uint32_t)(384 + c0));
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const int col = c0 + j;
+            const float4 hp4 = x_load4(c.X, row, col >> 2);
+            const float4 bir = __ldg(reinterpret_cast<const float4 *>(bi + col)), bhr = __ldg(reinterpret_cast<const float4 *>(bh + col));
+            const float4 biz = __ldg(reinterpret_cast<const float4 *>(bi + E + col)), bhz = __ldg(reinterpret_cast<const float4 *>(bh + E + col));
+            const float4 bin = __ldg(reinterpret_cast<const float4 *>(bi + 2 * E + col)), bhn = __ldg(reinterpret_cast<const float4 *>(bh + 2 * E + col));
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (want_value) wv = __ldg(reinterpret_cast<const float4 *>(na->head_w_eff + col));
+            const float hp[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+            const float f_bir[4] = {bir.x, bir.y, bir.z, bir.w}, f_bhr[4] = {bhr.x, bhr.y, bhr.z, bhr.w};
+            const float f_biz[4] = {biz.x, biz.y, biz.z, biz.w}, f_bhz[4] = {bhz.x, bhz.y, bhz.z, bhz.w};
+            const float f_bin[4] = {bin.x, bin.y, bin.z, bin.w}, f_bhn[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
+            const float f_w[4] = {wv.x, wv.y, wv.z, wv.w};
+            float hn[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float r = fast_sigmoid((__uint_as_float(ar[j + q]) + f_bir[q]) + f_bhr[q]);
+                const float z = fast_sigmoid((__uint_as_float(az[j + q]) + f_biz[q]) + f_bhz[q]);
+                const float n = fast_tanh((__uint_as_float(an[j + q]) + f_bin[q]) + r * (__uint_as_float(ahn[j + q]) + f_bhn[q]));
+                hn[q] = (1.f - z) * n + z * hp[q];
+                vdot = fmaf(f_w[q], hn[q], vdot);
+            }
+            x_store4(c.X, row, col >> 2, make_float4(hn[0], hn[1], hn[2], hn[3]));
+        }
+    }
+    if (want_value) c.s_val[hh * ROWS + row] = vdot;
+    worker_sync();
+    copy_out(c, na->hidden + (int64_t)l * c.a->R * E);
+    if (want_value && hh == 0 && c.a->value) {
+        int64_t gr;
+        int env, i;
+        if (row_info(c, row, gr, env, i)) c.a->value[gr] = (c.s_val[row] + c.s_val[ROWS + row]) + __ldg(na->head_b);
+    }
+}
+
+// ---- epilogue: actor head (softmax -> sample / argmax -> log-prob), same arithmetic and RNG as act_head_kernel -----------
+template <int A>
+__device__ void epi_head(const Ctx &c)
+{
+    if (c.warp >= 4) return;
+    const int row = 32 * c.warp + c.lane;
+    int64_t gr;
+    int env, i;
+    const bool ok = row_info(c, row, gr, env, i);
+    uint32_t v[16];
+    PF_TMEM_LD16(v, c.tmem + ((uint32_t)(32 * c.warp) << 16));
+    tmem_wait_ld();
+    if (!ok) return;
+    float z[A], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < A; ++k) { z[k] = __uint_as_float(v[k]) + __ldg(c.na->head_b + k); mx = fmaxf(mx, z[k]); }
+    float sm[A], den = 0.f;
+#pragma unroll
+    for (int k = 0; k < A; ++k) { sm[k] = expf(z[k] - mx); den += sm[k]; }
+    float psum = 0.f;
+#pragma unroll
+    for (int k = 0; k < A; ++k) { sm[k] /= den; psum += sm[k]; }
+    int act = 0;
+    if (c.a->force_action) {
+        act = min(max(c.a->action[gr], 0), A - 1);          // teacher forcing: log-prob of a given action
+    } else if (c.a->deterministic) {
+        float best = -1.f;
+#pragma unroll
+        for (int k = 0; k < A; ++k) if (sm[k] > best) { best = sm[k]; act = k; }
+    } else {
+        const uint64_t hsh = splitmix64(c.a->seed ^ splitmix64((uint64_t)gr * 0x100000001B3ull + (uint64_t)c.a->t));
+        const float u = (float)(hsh >> 40) * (1.0f / 16777216.0f) * psum;
+        float cs = 0.f;
+        act = A - 1;
+#pragma unroll
+        for (int k = 0; k < A; ++k) { cs += sm[k]; if (u < cs) { act = k; break; } }
+    }
+    const float ceps = 1.1920928955078125e-07f;
+    float lpa = 0.f;
+#pragma unroll
+    for (int k = 0; k < A; ++k) if (k == act) lpa = logf(fminf(fmaxf(sm[k] / psum, ceps), 1.f - ceps));
+    if (c.a->action && !c.a->force_action) c.a->action[gr] = act;
+    if (c.a->logp) c.a->logp[gr] = lpa;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+policy_step_kernel(const __grid_constant__ StepArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();          // SWIZZLE_128B atoms need 1024-byte alignment
+    unsigned char *X = smem;
+    unsigned char *Wst = smem + X_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + X_BYTES + NSTAGE * WSTAGE);   // full[NSTAGE], empty[NSTAGE], a_ready, mma_done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    float4 *s_p = reinterpret_cast<float4 *>(bars + 16);                                  // 128 x float4 (later: s_val)
+    float4 *s_e = s_p + ROWS;                                                               // 32 x float4
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int net, tile;
+    if (a.net_count == 2) { net = (int)blockIdx.x < a.n_tiles ? 1 : 0; tile = (int)blockIdx.x % a.n_tiles; }   // critic items first
+    else { net = a.net_first; tile = blockIdx.x; }
+    const NetArgs *na = &a.net[net];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);            // full: one arrive.expect_tx + the bulk copy's bytes
+            mbar_init(smem_u32(&bars[NSTAGE + s]), 1);   // empty: one tcgen05.commit
+        }
+        mbar_init(smem_u32(&bars[BAR_A_READY]), WORKERS);   // a_ready
+        mbar_init(smem_u32(&bars[BAR_MMA_DONE]), 1);        // mma_done
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ================================================================================= workers
+        Ctx c;
+        c.a = &a; c.na = na; c.X = X; c.row0 = (int64_t)tile * a.rows_per_tile; c.warp = warp; c.lane = lane;
+        c.tmem = tmem_base; c.bar_a_ready = smem_u32(&bars[BAR_A_READY]); c.bar_mma_done = smem_u32(&bars[BAR_MMA_DONE]); c.group = 0; c.s_p = s_p; c.s_e = s_e; c.s_val = reinterpret_cast<float *>(s_p);
+        {   // fp32 copies of the tile's pursuer / evader states (converted once; every SIMT phase reads them from smem)
+            const int t = threadIdx.x;
+            if (t < ROWS) {
+                int64_t gr;
+                int env, i;
+                s_p[t] = row_info(c, t, gr, env, i) ? load_p(&a, gr) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else if (t < ROWS + 32) {
+                const int64_t env = c.row0 / a.N + (t - ROWS);
+                s_e[t - ROWS] = (ROWS / a.N <= 32 && t - ROWS < ROWS / a.N && env < a.B) ? load_e(&a, (int)env) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            worker_sync();
+        }
+        long long tk[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) tk[q] = 0;
+        long long t_prev = clock64();
+        const long long t_begin = t_prev;
+#define PF_TICK(slot) do { const long long now_ = clock64(); tk[slot] += now_ - t_prev; t_prev = now_; } while (0)
+        for (int r = 0; r < 3; ++r) {
+            phase_msg(c, r);
+            PF_TICK(0 + r);
+            hand_over(c);                                              // AGG_vertex_0 -> acc @0
+            PF_TICK(11);
+            epi_store(c, 0, na->b_av, true, nullptr, 0, nullptr);
+            PF_TICK(3);
+            hand_over(c);                                              // semantic, K-slice r -> acc @128
+            PF_TICK(11);
+        }
+        epi_store(c, 128, na->b_sem, false, na->sem_w, na->sem_ld, nullptr);    // h0 (no activation)
+        PF_TICK(4);
+        for (int k = 0; k < a.depth; ++k) {
+            hand_over(c);                                              // FCRA_k, h part -> acc @128
+            PF_TICK(11);
+            phase_fcra(c, k);
+            PF_TICK(5);
+            hand_over(c);                                              // AGG_fcra_k -> acc @0
+            PF_TICK(11);
+            epi_store(c, 0, na->b_aggf[k], true, nullptr, 0, nullptr);
+            PF_TICK(6);
+            hand_over(c);                                              // FCRA_k, m part -> acc @128 (+=)
+            PF_TICK(11);
+            epi_store(c, 128, na->b_f[k], true, nullptr, 0, k == a.depth - 1 ? na->emb_out : nullptr);
+            PF_TICK(7);
+        }
+        for (int l = 0; l < 2; ++l) {
+            hand_over(c);                                              // W_ih: r @0, z @128, n @256
+            PF_TICK(11);
+            phase_load_hidden(c, l);
+            PF_TICK(8);
+            hand_over(c);                                              // W_hh: r += , z +=, hn @384
+            PF_TICK(11);
+            epi_cell(c, l, l == 1 && na->head_w_eff != nullptr);
+            PF_TICK(9);
+        }
+        if (net == 0) {
+            hand_over(c);                                              // actor head, n_out = 16 -> acc @0
+            PF_TICK(11);
+            epi_head<MARL_NUM_ACTIONS>(c);
+            PF_TICK(10);
+        }
+        if (a.dbg && threadIdx.x == 0) {
+            tk[12] = clock64() - t_begin;
+            for (int q = 0; q < 16; ++q) a.dbg[(size_t)blockIdx.x * 16 + q] = tk[q];
+        }
+    } else if (warp == 8) {
+        // ================================================================================= weight loader
+        if (lane == 0) {
+            int it = 0;
+            for (int u = 0; u < na->n_units; ++u) {
+                const Unit un = na->u[u];
+                const uint32_t bytes = 2u * un.n_out * 128u;
+                for (int kb = 0; kb < 4; ++kb, ++it) {
+                    const int s = it % NSTAGE, round = it / NSTAGE;
+                    if (round > 0) mbar_wait(smem_u32(&bars[NSTAGE + s]), (uint32_t)((round - 1) & 1));
+                    mbar_expect_tx(smem_u32(&bars[s]), bytes);
+                    bulk_g2s(smem_u32(Wst + s * WSTAGE), na->packed + un.off + (size_t)kb * bytes, bytes, smem_u32(&bars[s]));
+                }
+            }
+        }
+    } else {
+        // ================================================================================= MMA issuer
+        if (lane == 0) {
+            int it = 0, group = 0;
+            bool fresh_group = true;
+            for (int u = 0; u < na->n_units; ++u) {
+                const Unit un = na->u[u];
+                if (fresh_group) {
+                    mbar_wait(smem_u32(&bars[BAR_A_READY]), (uint32_t)(group & 1));
+                    tc_fence_after();
+                    fresh_group = false;
+                }
+                const uint32_t idesc = idesc_tf32(un.n_out);
+                const uint32_t acc = tmem_base + un.acc_col;
+                const uint32_t lo_off = (uint32_t)un.n_out * 128u;
+                for (int kb = 0; kb < 4; ++kb, ++it) {
+                    const int s = it % NSTAGE, round = it / NSTAGE;
+                    mbar_wait(smem_u32(&bars[s]), (uint32_t)(round & 1));
+                    tc_fence_after();
+                    const uint32_t xa = smem_u32(X + kb * XKB), wb = smem_u32(Wst + s * WSTAGE);
+                    // descriptors of the first K=8 slice; the next slices are +32 bytes = +2 in the (addr >> 4) field
+                    const uint64_t a_hi0 = make_desc(xa), a_lo0 = make_desc(xa + TILE), b_hi0 = make_desc(wb), b_lo0 = make_desc(wb + lo_off);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t a_hi = a_hi0 + 2 * kk, a_lo = a_lo0 + 2 * kk, b_hi = b_hi0 + 2 * kk, b_lo = b_lo0 + 2 * kk;
+                        umma_tf32(acc, a_hi, b_hi, idesc, (un.accumulate || kb || kk) ? 1u : 0u);
+                        umma_tf32(acc, a_lo, b_hi, idesc, 1u);
+                        umma_tf32(acc, a_hi, b_lo, idesc, 1u);
+                    }
+                    umma_commit(smem_u32(&bars[NSTAGE + s]));
+                }
+                if (un.last) {
+                    umma_commit(smem_u32(&bars[BAR_MMA_DONE]));
+                    ++group;
+                    fresh_group = true;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ---- weight packing: one unit = W[rows, k0 : k0+128] -> 4 k-blocks x (hi plane, lo plane) in the smem image ------------------
+__global__ void __launch_bounds__(256)
+pack_unit_kernel(const float *__restrict__ W, int64_t ld, int rows_valid, int n_out, int k0, unsigned char *__restrict__ out)
+{
+    const int idx = blockIdx.x * 256 + threadIdx.x;      // (n, k)
+    if (idx >= n_out * 128) return;
+    const int n = idx >> 7, k = idx & 127;
+    const float v = n < rows_valid ? W[(int64_t)n * ld + k0 + k] : 0.f;
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    const int kb = k >> 5, kk = k & 31;
+    const size_t plane = (size_t)n_out * 128;
+    const size_t off = (size_t)kb * 2 * plane + (size_t)n * 128 + ((((kk >> 2) ^ (n & 7))) << 4) + (kk & 3) * 4;
+    *reinterpret_cast<float *>(out + off) = hi;
+    *reinterpret_cast<float *>(out + off + plane) = lo;
+}
+
+struct UnitSrc {
+    const float *W;
+    int64_t ld;
+    int rows, n_out, k0, acc_col, accumulate, last;
+};
+
+static int build_units(const marl_dhgn_weights *w, int depth, int is_actor, int A, UnitSrc *us)
+{
+    int n = 0;
+    auto add = [&](const float *W, int64_t ld, int rows, int n_out, int k0, int acc, int accu, int last) {
+        us[n++] = UnitSrc{W, ld, rows, n_out, k0, acc, accu, last};
+    };
+    for (int r = 0; r < 3; ++r) {
+        add(w->agg_v_w, E, E, E, 0, 0, 0, 1);
+        add(w->sem_w, 3 * E + 4, E, E, 4 + E * r, 128, r > 0, 1);
+    }
+    for (int k = 0; k < depth; ++k) {
+        add(w->fcra_w[k], 2 * E, E, E, E, 128, 0, 1);
+        add(w->agg_f_w[k], E, E, E, 0, 0, 0, 1);
+        add(w->fcra_w[k], 2 * E, E, E, 0, 128, 1, 1);
+    }
+    for (int l = 0; l < 2; ++l) {
+        for (int g = 0; g < 3; ++g) add(w->gru_w_ih[l] + (int64_t)g * E * E, E, E, E, 0, 128 * g, 0, g == 2);
+        add(w->gru_w_hh[l], E, E, E, 0, 0, 1, 0);
+        add(w->gru_w_hh[l] + (int64_t)E * E, E, E, E, 0, 128, 1, 0);
+        add(w->gru_w_hh[l] + (int64_t)2 * E * E, E, E, E, 0, 384, 0, 1);
+    }
+    if (is_actor) add(w->head_w, E, A, 16, 0, 0, 0, 1);
+    return n;
+}
+
+static int64_t unit_bytes(int n_out) { return (int64_t)n_out * 1024; }
+
+static int check_weights(const marl_dhgn_weights *w, int depth, int is_actor)
+{
+    MARL_REQUIRE(w != nullptr, "marl_policy: weights struct is NULL");
+    MARL_REQUIRE(depth >= 1 && depth <= MAXD, "marl_policy: depth=%d unsupported (1..%d)", depth, MAXD);
+    bool ok = w->agg_v_w && w->agg_v_b && w->sem_w && w->sem_b && w->head_b;
+    for (int r = 0; r < 3; ++r) ok = ok && w->msg_w[r] && w->msg_b[r];
+    for (int k = 0; k < depth; ++k) ok = ok && w->agg_f_w[k] && w->agg_f_b[k] && w->fcra_w[k] && w->fcra_b[k];
+    for (int l = 0; l < 2; ++l) ok = ok && w->gru_w_ih[l] && w->gru_w_hh[l] && w->gru_b_ih[l] && w->gru_b_hh[l];
+    ok = ok && w->head_w;
+    MARL_REQUIRE(ok, "marl_policy: null weight pointer (%s)", is_actor ? "actor" : "critic");
+    return MARL_OK;
+}
+
+}  // namespace pf
+}  // namespace marl
+
+using namespace marl;
+
+extern "C" int64_t marl_policy_pack_bytes(int32_t depth, int32_t is_actor)
+{
+    if (depth < 1 || depth > pf::MAXD) return -1;
+    return (int64_t)(6 + 3 * depth + 12) * pf::unit_bytes(pf::E) + (is_actor ? pf::unit_bytes(16) : 0);
+}
+
+extern "C" int marl_policy_pack(const marl_dhgn_weights *w, int32_t depth, int32_t is_actor, int32_t action_dim, void *d_packed,
+                                void *stream)
+{
+    int rc = pf::check_weights(w, depth, is_actor);
+    if (rc) return rc;
+    MARL_REQUIRE(d_packed && ((uintptr_t)d_packed & 1023) == 0, "marl_policy_pack: workspace must be 1024-byte aligned");
+    MARL_REQUIRE(!is_actor || (action_dim >= 1 && action_dim <= 16), "marl_policy_pack: action_dim=%d (1..16)", action_dim);
+    pf::UnitSrc us[pf::MAX_UNITS];
+    const int n = pf::build_units(w, depth, is_actor, action_dim, us);
+    unsigned char *out = static_cast<unsigned char *>(d_packed);
+    for (int u = 0; u < n; ++u) {
+        const int total = us[u].n_out * 128;
+        pf::pack_unit_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(us[u].W, us[u].ld, us[u].rows, us[u].n_out, us[u].k0, out);
+        rc = check_launch("pack_unit_kernel");
+        if (rc) return rc;
+        out += pf::unit_bytes(us[u].n_out);
+    }
+    return MARL_OK;
+}
+
+static int fill_net(pf::NetArgs &na, const marl_dhgn_weights *w, const marl_policy_net_io *io, int depth, int is_actor, int A)
+{
+    int rc = pf::check_weights(w, depth, is_actor);
+    if (rc) return rc;
+    MARL_REQUIRE(io->d_packed && io->d_hidden && io->d_emb_out, "marl_policy_rollout_step: null packed / hidden / emb_out (%s)",
+                 is_actor ? "actor" : "critic");
+    pf::UnitSrc us[pf::MAX_UNITS];
+    na.n_units = pf::build_units(w, depth, is_actor, A, us);
+    uint32_t off = 0;
+    for (int u = 0; u < na.n_units; ++u) {
+        na.u[u] = pf::Unit{off, (uint16_t)us[u].n_out, (uint16_t)us[u].acc_col, (uint8_t)us[u].accumulate, (uint8_t)us[u].last, 0};
+        off += (uint32_t)pf::unit_bytes(us[u].n_out);
+    }
+    na.packed = static_cast<const unsigned char *>(io->d_packed);
+    for (int r = 0; r < 3; ++r) { na.msg_w[r] = w->msg_w[r]; na.msg_b[r] = w->msg_b[r]; }
+    na.b_av = w->agg_v_b; na.sem_w = w->sem_w; na.b_sem = w->sem_b; na.sem_ld = 3 * pf::E + 4;
+    for (int k = 0; k < pf::MAXD; ++k) {
+        na.b_aggf[k] = k < depth ? w->agg_f_b[k] : nullptr;
+        na.b_f[k] = k < depth ? w->fcra_b[k] : nullptr;
+        na.hist[k] = k < depth ? io->d_hist[k] : nullptr;
+    }
+    for (int l = 0; l < 2; ++l) { na.b_ih[l] = w->gru_b_ih[l]; na.b_hh[l] = w->gru_b_hh[l]; }
+    na.head_b = w->head_b;
+    na.head_w_eff = is_actor ? nullptr : w->head_w;
+    na.emb_out = io->d_emb_out;
+    na.hidden = io->d_hidden;
+    na.all_ones = is_actor ? 0 : 1;
+    return MARL_OK;
+}
+
+extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dhgn_weights *actor_w, const marl_policy_net_io *actor_io,
+                                        const marl_dhgn_weights *critic_w, const marl_policy_net_io *critic_io, void *stream)
+{
+    MARL_REQUIRE(s != nullptr, "marl_policy_rollout_step: step struct is NULL");
+    MARL_REQUIRE(s->E == pf::E, "marl_policy_rollout_step: embedding_dim=%d (the fused kernel is built for 128)", s->E);
+    MARL_REQUIRE(s->B > 0 && s->N >= 1 && s->N <= 128 && s->O >= 1 && s->depth >= 1 && s->depth <= pf::MAXD,
+                 "marl_policy_rollout_step: B=%d N=%d O=%d depth=%d", s->B, s->N, s->O, s->depth);
+    MARL_REQUIRE(s->action_dim == MARL_NUM_ACTIONS, "marl_policy_rollout_step: action_dim=%d (9)", s->action_dim);
+    MARL_REQUIRE(s->d_p_state && s->d_e_state && s->d_oxy && s->d_o_count && s->d_p_adj_bits && s->d_e_adj && s->d_o_adj_bits,
+                 "marl_policy_rollout_step: null observation pointer");
+    MARL_REQUIRE((actor_w && actor_io) || (critic_w && critic_io), "marl_policy_rollout_step: no network given");
+    pf::StepArgs a{};
+    a.B = s->B; a.N = s->N; a.O = s->O; a.NW = (s->N + 31) / 32; a.OW = (s->O + 31) / 32; a.depth = s->depth; a.A = s->action_dim;
+    a.rows_per_tile = (pf::ROWS / s->N) * s->N;
+    a.R = (int64_t)s->B * s->N;
+    a.n_tiles = (int)((a.R + a.rows_per_tile - 1) / a.rows_per_tile);
+    a.p_state = s->d_p_state; a.e_state = s->d_e_state; a.oxy = s->d_oxy; a.map_id = s->d_map_id; a.o_count = s->d_o_count;
+    a.p_adj = s->d_p_adj_bits; a.e_adj = s->d_e_adj; a.o_adj = s->d_o_adj_bits;
+    a.action = s->d_action; a.logp = s->d_logp; a.value = s->d_value; a.seed = s->seed; a.t = s->t; a.deterministic = s->deterministic; a.force_action = s->force_action;
+    a.dbg = static_cast<long long *>(s->d_debug);
+    int rc;
+    if (actor_w && actor_io) { rc = fill_net(a.net[0], actor_w, actor_io, s->depth, 1, s->action_dim); if (rc) return rc; }
+    if (critic_w && critic_io) { rc = fill_net(a.net[1], critic_w, critic_io, s->depth, 0, s->action_dim); if (rc) return rc; }
+    const bool both = actor_w && actor_io && critic_w && critic_io;
+    a.net_count = both ? 2 : 1;
+    a.net_first = (actor_w && actor_io) ? 0 : 1;
+    cudaError_t e = cudaFuncSetAttribute(pf::policy_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pf::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("policy_step_kernel: smem %d: %s", pf::SMEM_BYTES, cudaGetErrorString(e)); return MARL_ECUDA; }
+    pf::policy_step_kernel<<<a.n_tiles * a.net_count, pf::THREADS, pf::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    return check_launch("policy_step_kernel");
+}

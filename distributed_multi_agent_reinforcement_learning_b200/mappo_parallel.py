@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 from torch.nn.utils import spectral_norm
 
-from . import _lib, policy_ops as ops
+from . import _lib, fused_policy, policy_ops as ops
 from .normalization import Normalization
 from .replay_buffer import BigBuffer, ReplayBuffer
 
@@ -483,7 +483,7 @@ class MAPPO:
 
     # ------------------------------------------------------------------------------------------------ rollout
     @torch.no_grad()
-    def rollout_batched(self, engine, arena, T=None, seed=0, deterministic=False, groups=1):
+    def rollout_batched(self, engine, arena, T=None, seed=0, deterministic=False, groups=1, use_fused=None, timers=None):
         """MAPPO.run_episode (:742-827) for all B envs of a BatchedPursuitEnv at once, entirely on the GPU.
         Per step: observe kernel -> fused encoder (actor, then critic with all-ones adjacency) -> GRU cell -> heads ->
         closed-loop env kernel (evader move + pursuer step + reward-norm + store).  Fills `arena` plus the history /
@@ -520,6 +520,38 @@ class MAPPO:
             w_eff = w.reshape(E).contiguous()
             return emb_c, feat_c[0]
 
+        if use_fused is None:
+            use_fused = fused_policy.supported(self)
+        if use_fused:
+            # ONE launch per env step for both networks (csrc/policy_fused.cu); embeddings / values / log-probs / actions
+            # land directly in their rollout slabs.  The critic's effective head row is constant while the weights are
+            # (one power iteration on a [1,E] matrix is already converged), so it is computed once.
+            w, _ = self.critic.head_weight()
+            fused = fused_policy.FusedRolloutStep(self, w.reshape(E).contiguous())
+            oxy_i = engine.boundary_xy.contiguous()
+            none_if_zero = lambda lst: [None if h is zeros_hist else h for h in lst]   # noqa: E731
+            def timed(name, fn):
+                if timers is None:
+                    return fn()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                fn()
+                b_.record()
+                timers.setdefault(name, []).append((a_, b_))
+
+            for t in range(T):
+                timed("env_observe_kernel", engine.observe)
+                h_t = none_if_zero(history(t))
+                timed("policy_step_kernel", lambda: fused.step(engine, oxy_i, o_count, t, seed, deterministic, h_t, h_t,
+                                                               hist_a[t + D], hist_c[t + D], ha, hc, act[t], logp[t], v[t]))
+                engine.rollout_closed(arena, 1, t0=t, action_tape=act[t:t + 1], env_t0=t, groups=groups, timers=timers)
+            engine.observe()
+            h_fin = none_if_zero([hist_c[T - 1 + D]] + history(T - 1)[:D - 1])
+            scratch = torch.empty(B, N, E, **f32)
+            fused.step(engine, oxy_i, o_count, T, seed, deterministic, h_fin, h_fin, scratch, scratch, ha, hc, None, None, v[T],
+                       nets=("critic",))
+            return self._train_batch(engine, arena, T, oxy, hist_a, hist_c, v, logp)
+
         for t in range(T):
             engine.observe()
             graph = ops.GraphBatch(engine.p_state.to(torch.float32), engine.e_state.to(torch.float32), oxy, engine.map_id,
@@ -541,6 +573,10 @@ class MAPPO:
         feat_c, hc = self.critic.features(emb_c.view(1, B * N, E), hc)
         w, _ = self.critic.head_weight()
         v[T] = torch.nn.functional.linear(feat_c[0], w, self.critic.Mean.bias).view(B, N)
+        return self._train_batch(engine, arena, T, oxy, hist_a, hist_c, v, logp)
+
+    def _train_batch(self, engine, arena, T, oxy, hist_a, hist_c, v, logp):
+        B, D, dev = engine.B, self.depth, self.device
         oxy_env = oxy[engine.map_id.long()].contiguous()
         return TrainBatch(p=arena.p_state_f32[:T], e=arena.e_state_f32[:T, :, 0].contiguous(), oxy=oxy_env,
                           o_count_train=torch.full((B,), engine.O, dtype=torch.int32, device=dev),

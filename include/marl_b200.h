@@ -308,6 +308,51 @@ int marl_gemm_tf32x3(int32_t M, int32_t N, int32_t K1, int32_t K2, const float *
                      int64_t lda2, const float *d_W, int64_t ldw, const float *d_bias, const float *d_D, int64_t ldd,
                      float *d_C, int64_t ldc, int32_t relu, void *stream);
 
+/* ---- fused rollout step of the DHGN actor / critic (tcgen05 + TMEM, one launch per env step) -------------------------------
+ * Replaces, for all B envs at once, the network half of the rollout body DHGN/mappo_parallel.py:758-801:
+ * actor.choose_action (:440-449) and critic.forward mode 0 (:510-514) — encoder (DHGN :235-348), nn.GRU step, heads.
+ * All pointers are device pointers in the nn.Module layouts ([out,in] row-major).  E = embedding_dim must be 128, the GRU
+ * has 2 layers, depth = algo.depth in 1..3.  For the critic, head_w is the EFFECTIVE [1,E] row (weight_orig / sigma of
+ * torch.nn.utils.spectral_norm) and "all ones" adjacency is used (:64-65) over the o_count real obstacle cells. */
+typedef struct marl_dhgn_weights {
+    const float *msg_w[3], *msg_b[3];          /* MSG_layers.{0,1,2}: [E,8], [E,4], [E,4] */
+    const float *agg_v_w, *agg_v_b;            /* AGG_layers.AGG_vertex_0 [E,E] */
+    const float *sem_w, *sem_b;                /* semantic_layer [E, 3E+4] */
+    const float *agg_f_w[3], *agg_f_b[3];      /* AGG_layers.AGG_fcra_k [E,E] */
+    const float *fcra_w[3], *fcra_b[3];        /* FCRA_layers.k [E,2E] */
+    const float *gru_w_ih[2], *gru_w_hh[2], *gru_b_ih[2], *gru_b_hh[2];   /* nn.GRU [3E,E], [3E] */
+    const float *head_w, *head_b;              /* actor Mean [A,E],[A]; critic effective row [1,E],[1] */
+} marl_dhgn_weights;
+typedef struct marl_policy_net_io {
+    const void *d_packed;        /* marl_policy_pack output (1024-byte aligned, marl_policy_pack_bytes bytes) */
+    const float *d_hist[3];      /* history embeddings [B,N,E], k = 0 the most recent; NULL = zeros (:750-752) */
+    float *d_emb_out;            /* [B,N,E] this step's embedding (stored at t+D of the history buffer) */
+    float *d_hidden;             /* [2, B*N, E] GRU hidden state, updated in place */
+} marl_policy_net_io;
+typedef struct marl_policy_step {
+    int32_t B, N, O, E, depth, action_dim, t, deterministic;
+    int32_t force_action;        /* != 0: d_action is an INPUT (teacher forcing); d_logp is the log-prob of that action */
+    int32_t reserved;
+    uint64_t seed;               /* sampling: same counter RNG as marl_act_head (keyed by seed, row, t) */
+    const double *d_p_state;     /* [B,N,4] */
+    const double *d_e_state;     /* [B,4] */
+    const int32_t *d_oxy;        /* [M,O,2] boundary cells per map (marl_raser_map_build) */
+    const int32_t *d_map_id;     /* [B] or NULL */
+    const int32_t *d_o_count;    /* [M] real boundary cells per map, clamped to O */
+    const uint32_t *d_p_adj_bits; const uint8_t *d_e_adj; const uint32_t *d_o_adj_bits;   /* marl_env_observe outputs */
+    int32_t *d_action;           /* [B,N] out (actor) */
+    float *d_logp;               /* [B,N] out (actor) */
+    float *d_value;              /* [B,N] out (critic) */
+    void *d_debug;               /* NULL, or i64 [grid,16] per-CTA phase cycle counters (profiling aid) */
+} marl_policy_step;
+/* Pre-splits (hi/lo TF32) and pre-swizzles every dense layer of one network into the shared-memory image the fused kernel
+ * streams; call once per weight update. */
+int64_t marl_policy_pack_bytes(int32_t depth, int32_t is_actor);
+int marl_policy_pack(const marl_dhgn_weights *w, int32_t depth, int32_t is_actor, int32_t action_dim, void *d_packed, void *stream);
+/* One env step of both networks (either pair may be NULL to run only the other, e.g. the critic-only bootstrap :806-825). */
+int marl_policy_rollout_step(const marl_policy_step *s, const marl_dhgn_weights *actor_w, const marl_policy_net_io *actor_io,
+                             const marl_dhgn_weights *critic_w, const marl_policy_net_io *critic_io, void *stream);
+
 /* torch.nn.utils.clip_grad_norm_ (:710-711) and torch.optim.Adam.step (runner.py:72-78) on flat fp32 arenas. */
 int64_t marl_clip_workspace_bytes(int64_t n);
 int marl_clip_grad_norm(int64_t n, float *d_grad, float max_norm, void *d_workspace, float *d_total_norm, void *stream);

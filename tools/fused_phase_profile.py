@@ -1,0 +1,51 @@
+"""Profiling aid: per-phase cycle counters of the fused policy step kernel (marl_policy_step.d_debug) at the bench shape."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from distributed_multi_agent_reinforcement_learning_b200.fused_policy import FusedRolloutStep  # noqa: E402
+from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO  # noqa: E402
+from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv  # noqa: E402
+
+cfg = bench.make_cfg()
+B, M, N, E = bench.B_PER_GPU, 32, bench.N_AGENTS, 128
+wl = bench.host_workload(cfg, B, M, seed=1)
+env = BatchedPursuitEnv(cfg, B, num_maps=M)
+env.set_maps(wl["grids"], wl["inflated"])
+env.set_state(wl["p_state"], wl["e_state"], wl["target"], wl["map_id"], time_step=0)
+env.set_target_tape(wl["tape"])
+env.start_episode()
+torch.manual_seed(0)
+m = MAPPO(cfg, B, B // 10, "Learner")
+w, _ = m.critic.head_weight()
+fused = FusedRolloutStep(m, w.reshape(E).contiguous())
+dev = env.device
+oxy_i = env.boundary_xy.contiguous()
+o_count = torch.clamp(env.boundary_count, max=env.O).contiguous()
+ha, hc = torch.zeros(2, B * N, E, device=dev), torch.zeros(2, B * N, E, device=dev)
+emb_a, emb_c = torch.empty(B, N, E, device=dev), torch.empty(B, N, E, device=dev)
+act, logp, val = torch.zeros(B, N, dtype=torch.int32, device=dev), torch.empty(B, N, device=dev), torch.empty(B, N, device=dev)
+hist = [0.1 * torch.randn(B, N, E, device=dev)]
+env.observe()
+n_tiles = (B * N + 127) // 128
+dbg = torch.zeros(2 * n_tiles, 16, dtype=torch.int64, device=dev)
+for it in range(3):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    fused.step(env, oxy_i, o_count, it, 1, False, hist, hist, emb_a, emb_c, ha, hc, act, logp, val, debug=dbg)
+    e.record()
+    e.synchronize()
+    print("launch ms", s.elapsed_time(e))
+d = dbg.cpu().numpy().astype(np.float64)
+names = ["msg0", "msg1", "msg2", "epi_av(x3)", "epi_sem", "fcra", "epi_aggf", "epi_f", "load_hidden(x2)", "epi_cell(x2)", "head",
+         "wait_mma(all)", "total"]
+for label, rows in (("critic", d[:n_tiles]), ("actor", d[n_tiles:])):
+    print(label, "tiles", len(rows))
+    for i, n in enumerate(names):
+        print(f"   {n:18s} {rows[:, i].mean():10.0f} cycles  ({100 * rows[:, i].mean() / rows[:, 12].mean():5.1f}%)")
