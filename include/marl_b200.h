@@ -353,6 +353,18 @@ int marl_policy_pack(const marl_dhgn_weights *w, int32_t depth, int32_t is_actor
 int marl_policy_rollout_step(const marl_policy_step *s, const marl_dhgn_weights *actor_w, const marl_policy_net_io *actor_io,
                              const marl_dhgn_weights *critic_w, const marl_policy_net_io *critic_io, void *stream);
 
+/* ---- second network family: GnnExtractor (obstacle_differ_3hop/mappo_parallel.py:34-70) -------------------------------------
+ * L1-normalised adjacency-weighted mean over entities (F.normalize(adj, p=1) then adj @ x, :55-66).  rows = S*N (sample, agent)
+ * rows; adj f32 [rows, J] (J = N + O entities); element (s,i,j,:) of x lives at s*sample_stride + i*agent_stride +
+ * j*entity_stride floats, j < jmax <= J (h0: dense [S,N,J,E] => strides (N*J*E, J*E, E), jmax = J; last_comm_embedding
+ * [S,N,2E] shared by all agents of a sample => strides (N*2E, 0, 2E), jmax = N).  The weights are always normalised over all J
+ * entities.  all_ones != 0: the critic's ones_like(adj) (:171).  E in {32, 64, 128, 256}.  bwd: d x for the dense h0 layout. */
+int marl_entity_agg_fwd(int64_t rows, int32_t N, int32_t J, int32_t jmax, int32_t E, const float *d_adj, int32_t all_ones,
+                        const float *d_x, int64_t sample_stride, int64_t agent_stride, int64_t entity_stride, float *d_out,
+                        void *stream);
+int marl_entity_agg_bwd(int64_t rows, int32_t J, int32_t E, const float *d_adj, int32_t all_ones, const float *d_dout, float *d_dx,
+                        void *stream);
+
 /* torch.nn.utils.clip_grad_norm_ (:710-711) and torch.optim.Adam.step (runner.py:72-78) on flat fp32 arenas. */
 int64_t marl_clip_workspace_bytes(int64_t n);
 int marl_clip_grad_norm(int64_t n, float *d_grad, float max_norm, void *d_workspace, float *d_total_norm, void *stream);
