@@ -539,12 +539,33 @@ class MAPPO:
                 b_.record()
                 timers.setdefault(name, []).append((a_, b_))
 
+            # The A* replanning due every `difficulty` steps only needs the env state, not the action: it runs on a side
+            # stream concurrently with the policy kernel (its long tail of slow searches then costs no wall time) and is
+            # joined before the env kernel consumes the paths.
+            overlap = timers is None and groups == 1
+            main = torch.cuda.current_stream()
+            if overlap:
+                if getattr(engine, "_replan_stream", None) is None:
+                    engine._replan_stream = torch.cuda.Stream(device=dev)
+                side = engine._replan_stream
+            diff = int(engine.params.difficulty)
             for t in range(T):
+                join = None
+                if overlap and t % diff == 0:
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    side.wait_event(fork)
+                    engine.evader_replan(0, B, side)
+                    join = torch.cuda.Event()
+                    join.record(side)
                 timed("env_observe_kernel", engine.observe)
                 h_t = none_if_zero(history(t))
                 timed("policy_step_kernel", lambda: fused.step(engine, oxy_i, o_count, t, seed, deterministic, h_t, h_t,
                                                                hist_a[t + D], hist_c[t + D], ha, hc, act[t], logp[t], v[t]))
-                engine.rollout_closed(arena, 1, t0=t, action_tape=act[t:t + 1], env_t0=t, groups=groups, timers=timers)
+                if join is not None:
+                    main.wait_event(join)
+                engine.rollout_closed(arena, 1, t0=t, action_tape=act[t:t + 1], env_t0=t, groups=groups, timers=timers,
+                                      skip_replan=join is not None)
             engine.observe()
             h_fin = none_if_zero([hist_c[T - 1 + D]] + history(T - 1)[:D - 1])
             scratch = torch.empty(B, N, E, **f32)

@@ -264,7 +264,7 @@ class BatchedPursuitEnv:
             "marl_rollout_closed")
         self.launches += 1
 
-    def rollout_closed(self, arena, K, t0=0, action_tape=None, seed=0, env_t0=0, timers=None, groups=1):
+    def rollout_closed(self, arena, K, t0=0, action_tape=None, seed=0, env_t0=0, timers=None, groups=1, skip_replan=False):
         """K closed-loop env iterations with the A* evader on the GPU.  The evader's per-step move is fused into the
         rollout kernel; replanning is one launch per `difficulty` steps, so K steps are 2*ceil(K/difficulty) launches
         per group.  `env_t0` is the (lock-step) env time_step at entry.
@@ -273,7 +273,9 @@ class BatchedPursuitEnv:
         CUDA stream: a search that takes 100x longer than the median (A* is a long-tailed workload) then only holds
         up its own sub-batch while the other chains keep the SMs busy.  Results are identical for any grouping.
         Nothing touches the host, so the whole thing can be captured in a CUDA graph (EpisodeGraph).
-        timers: optional dict name -> list of (start_event, end_event) around every launch (groups == 1 only)."""
+        timers: optional dict name -> list of (start_event, end_event) around every launch (groups == 1 only).
+        skip_replan: the caller has already launched evader_replan for this boundary (e.g. on a side stream, overlapped
+        with the policy kernel) and joined it."""
         assert arena.B == self.B
         if action_tape is not None:
             assert tuple(action_tape.shape) == (K, self.B, self.N) and action_tape.dtype == torch.int32
@@ -295,7 +297,7 @@ class BatchedPursuitEnv:
             k = 0
             while k < K:
                 ts = env_t0 + k
-                if ts % D == 0:
+                if ts % D == 0 and not skip_replan:
                     ev = mark("evader_kernel(replan)")
                     self.evader_replan(lo, hi, stream)
                     if ev:
