@@ -88,6 +88,10 @@ _PROTOTYPES = {
     "marl_policy_rollout_step": (C.c_int, [_VP] * 6),
     "marl_entity_agg_fwd": (C.c_int, [_I64, _I32, _I32, _I32, _I32, _VP, _I32, _VP, _I64, _I64, _I64, _VP, _VP]),
     "marl_entity_agg_bwd": (C.c_int, [_I64, _I32, _I32, _VP, _I32, _VP, _VP, _VP]),
+    "marl_gru_pack_bytes": (_I64, []),
+    "marl_gru_pack": (C.c_int, [_VP, _VP, _VP]),
+    "marl_gru_seq_fwd": (C.c_int, [_I32, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "marl_gru_seq_bwd": (C.c_int, [_I32, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "marl_clip_workspace_bytes": (_I64, [_I64]),
     "marl_clip_grad_norm": (C.c_int, [_I64, _VP, _F32, _VP, _VP, _VP]),
     "marl_adam_step": (C.c_int, [_I64, _VP, _VP, _VP, _VP, _F32, _F32, _F32, _F32, _I64, _VP]),

@@ -163,6 +163,19 @@ def fcra_agg(hist, p_adj_bits, all_ones, S, N, E, sample_stride=None, agent_stri
     return out
 
 
+USE_GRU_SEQ = True         # hidden size 128: the recurrence runs as one persistent kernel per direction (csrc/gru_seq.cu)
+
+
+def _gru_pack(w_hh):
+    """Pre-split / pre-swizzled images of W_hh for marl_gru_seq_{fwd,bwd} (1024-byte aligned)."""
+    nbytes = int(_L().marl_gru_pack_bytes())
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=w_hh.device)
+    off = (-buf.data_ptr()) % 1024
+    packed = buf[off:off + nbytes]
+    _lib.check(_L().marl_gru_pack(w_hh.detach().contiguous().data_ptr(), packed.data_ptr(), _lib.stream_ptr()), "marl_gru_pack")
+    return packed
+
+
 class _GRULayer(torch.autograd.Function):
     """One nn.GRU layer over a whole sequence: the input projection is one GEMM over all steps, the recurrence is
     one [R,E]x[E,3E] GEMM + one fused cell kernel per step."""
@@ -179,6 +192,17 @@ class _GRULayer(torch.autograd.Function):
             gi_all = torch.addmm(b_ih, x.view(T * R, E), w_ih.t()).view(T, R, 3 * E)
         out = torch.empty(T, R, E, dtype=x.dtype, device=x.device)
         saves = torch.empty(4, T, R, E, dtype=x.dtype, device=x.device) if need else None
+        if tc and E == 128 and USE_GRU_SEQ:
+            # whole recurrence in one persistent kernel (csrc/gru_seq.cu)
+            packed = _gru_pack(w_hh)
+            _lib.check(_L().marl_gru_seq_fwd(T, R, E, gi_all.data_ptr(), h0.contiguous().data_ptr(), packed.data_ptr(),
+                                             b_hh.contiguous().data_ptr(), out.data_ptr(), saves.data_ptr() if need else None,
+                                             _lib.stream_ptr()), "marl_gru_seq_fwd")
+            ctx.seq = True
+            if need:
+                ctx.save_for_backward(x, h0, w_ih, w_hh, out, saves, packed)
+            return out
+        ctx.seq = False
         gh = torch.empty(R, 3 * E, dtype=x.dtype, device=x.device)
         w_hh_t = w_hh.t()
         h = h0.contiguous()
@@ -198,6 +222,22 @@ class _GRULayer(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
+        if ctx.seq:
+            x, h0, w_ih, w_hh, out, saves, packed = ctx.saved_tensors
+            T, R, E = x.shape
+            d_out = d_out.contiguous()
+            dgi = torch.empty(T, R, 3 * E, dtype=x.dtype, device=x.device)
+            dgh = torch.empty(T, R, 3 * E, dtype=x.dtype, device=x.device)
+            dh0 = torch.empty(R, E, dtype=x.dtype, device=x.device)
+            h0c = h0.contiguous()
+            _lib.check(_L().marl_gru_seq_bwd(T, R, E, d_out.data_ptr(), saves.data_ptr(), out.data_ptr(), h0c.data_ptr(),
+                                             packed.data_ptr(), dgi.data_ptr(), dgh.data_ptr(), dh0.data_ptr(), _lib.stream_ptr()),
+                       "marl_gru_seq_bwd")
+            dgi2, dgh2 = dgi.view(T * R, 3 * E), dgh.view(T * R, 3 * E)
+            h_prev_all = torch.cat([h0c.unsqueeze(0), out[:-1]], dim=0).view(T * R, E)
+            w_ih_T = w_ih.t().contiguous()
+            dx = (_gemm_tc(dgi2, None, w_ih_T, None, None, False) if _tc_ok(dgi2, w_ih_T, None) else torch.mm(dgi2, w_ih)).view(T, R, E)
+            return dx, dh0, torch.mm(dgi2.t(), x.view(T * R, E)), torch.mm(dgh2.t(), h_prev_all), dgi2.sum(0), dgh2.sum(0)
         x, h0, w_ih, w_hh, out, saves = ctx.saved_tensors
         T, R, E = x.shape
         d_out = d_out.contiguous()

@@ -365,6 +365,20 @@ int marl_entity_agg_fwd(int64_t rows, int32_t N, int32_t J, int32_t jmax, int32_
 int marl_entity_agg_bwd(int64_t rows, int32_t J, int32_t E, const float *d_adj, int32_t all_ones, const float *d_dout, float *d_dx,
                         void *stream);
 
+/* ---- nn.GRU layer recurrence over a whole sequence, one persistent kernel per direction (hidden size 128) ----------------------
+ * Replaces the T-step loop inside torch.nn.GRU (SharedActor/SharedCritic.forward mode 1, DHGN/mappo_parallel.py:424-433,531-538)
+ * and its autograd backward.  gi f32 [T,R,3E] = x W_ih^T + b_ih for all steps (one GEMM by the caller); gate order r, z, n.
+ * marl_gru_pack pre-splits / pre-swizzles W_hh [3E,E] for both directions into d_packed (1024-byte aligned,
+ * marl_gru_pack_bytes() bytes).  fwd: out [T,R,E] (h_t), saves [4,T,R,E] = (r, z, n, W_hn h + b_hn) for the backward (may be
+ * NULL).  bwd: given d_out, writes dgi, dgh [T,R,3E] (the gradients w.r.t. gi and gh = h W_hh^T + b_hh, from which the caller
+ * forms dx, dW_ih, dW_hh and the bias gradients with plain GEMMs / reductions) and dh0 [R,E]. */
+int64_t marl_gru_pack_bytes(void);
+int marl_gru_pack(const float *d_w_hh, void *d_packed, void *stream);
+int marl_gru_seq_fwd(int32_t T, int64_t R, int32_t E, const float *d_gi, const float *d_h0, const void *d_packed,
+                     const float *d_b_hh, float *d_out, float *d_saves, void *stream);
+int marl_gru_seq_bwd(int32_t T, int64_t R, int32_t E, const float *d_dout, const float *d_saves, const float *d_out,
+                     const float *d_h0, const void *d_packed, float *d_dgi, float *d_dgh, float *d_dh0, void *stream);
+
 /* torch.nn.utils.clip_grad_norm_ (:710-711) and torch.optim.Adam.step (runner.py:72-78) on flat fp32 arenas. */
 int64_t marl_clip_workspace_bytes(int64_t n);
 int marl_clip_grad_norm(int64_t n, float *d_grad, float max_norm, void *d_workspace, float *d_total_norm, void *stream);

@@ -220,7 +220,7 @@ def test_fcra_agg_and_strided_history():
         torch.testing.assert_close(got1, hist.mean(1, keepdim=True).expand(-1, N, -1), rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("E,T,R", [(128, 9, 37), (32, 4, 5)])
+@pytest.mark.parametrize("E,T,R", [(128, 9, 37), (32, 4, 5), (128, 1, 64), (128, 23, 333)])
 def test_gru_layer_forward_backward(E, T, R):
     from distributed_multi_agent_reinforcement_learning_b200 import policy_ops as ops
     from oracle import policy_ref
@@ -233,7 +233,8 @@ def test_gru_layer_forward_backward(E, T, R):
     b = [t.clone().requires_grad_(True) for t in (x, h0, w["G.weight_ih_l0"], w["G.weight_hh_l0"], w["G.bias_ih_l0"], w["G.bias_hh_l0"])]
     wr = {"G.weight_ih_l0": b[2], "G.weight_hh_l0": b[3], "G.bias_ih_l0": b[4], "G.bias_hh_l0": b[5]}
     ref, _ = policy_ref.gru_layer(wr, "G", 0, b[0], b[1])
-    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+    # atol: 23 recurrent steps of fp32 GEMMs in a different summation order (3xTF32 tensor-core vs library sgemm)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=5e-6)
     # and against torch.nn.GRU itself (the module the reference uses)
     gru = torch.nn.GRU(E, E, 1).cuda()
     torch.backends.cudnn.allow_tf32 = False               # cuDNN's RNN path would otherwise round the GEMMs to TF32
@@ -241,7 +242,7 @@ def test_gru_layer_forward_backward(E, T, R):
         gru.weight_ih_l0.copy_(w["G.weight_ih_l0"]); gru.weight_hh_l0.copy_(w["G.weight_hh_l0"])
         gru.bias_ih_l0.copy_(w["G.bias_ih_l0"]); gru.bias_hh_l0.copy_(w["G.bias_hh_l0"])
         lib_out, _ = gru(x, h0.unsqueeze(0))
-    torch.testing.assert_close(out.detach(), lib_out, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out.detach(), lib_out, rtol=1e-4, atol=2e-5)
     dout = mk(T, R, E)
     out.backward(dout)
     ref.backward(dout)
