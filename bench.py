@@ -489,7 +489,8 @@ def run_ours(args):
     roofline = {"kernel": "policy_step_kernel (DHGN encoder + 2-layer GRU + heads of actor AND critic, one launch per env step; "
                           "tcgen05 kind::tf32, 3xTF32 split for fp32-level accuracy, accumulators in TMEM)",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16; kind::tf32 runs at half of it "
+                "traffic": 153.5e6, "traffic_source": "profiles/r1_policy_step_kernel_ncu_summary.txt (dram read + write of one launch, ncu --set full)",
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16; kind::tf32 runs at half of it "
                                                 "and the 3xTF32 split issues 3 MMAs per product, so this kernel's ceiling is frac = 1/6)",
                 "algorithmic_flops_per_launch": flops_launch, "flops_per_agent_per_network": policy_flops_per_agent(N, env.O, cfg.algo.depth),
                 "avg_launch_us": pk["avg_us"], "share_of_step": pk["total_ms"] / ms_episode,
