@@ -1,0 +1,211 @@
+// wgrad_tf32x3.cu — weight gradients of the dense layers on the tcgen05 tensor cores with fp32-level accuracy:
+//     dW[n][k] (+)= sum_r dY[r][n] * X[r][k]        (nn.Linear / nn.GRU weight gradients inside loss.backward(),
+//                                                    DHGN/mappo_parallel.py:708; r runs over the ~5e5 rows of a minibatch)
+// This is a GEMM whose reduction dimension is the (huge) row dimension and whose operands are both stored row-major
+// [rows, features], i.e. "MN-major" for the tensor core.  The producers therefore TRANSPOSE on the fly: 32 rows x 128
+// features of each operand are loaded with 32-byte-sector-exact global loads and written into the K-major SWIZZLE_128B
+// canonical layout ([128 features x 32 rows], hi and lo TF32 planes) with 4-byte stores arranged so that a warp covers an
+// 8 (features) x 4 (rows) patch = 32 distinct banks.  Split-K over row ranges (<= 64 k-blocks per CTA so that no TMEM
+// accumulator sees more than 128 truncating accumulate steps; main products alternate between two accumulators, the
+// 2^-11-small correction products go to a third, all summed in round-to-nearest fp32 by the epilogue), per-slice partial
+// tiles in a workspace, and a deterministic reduction kernel (no atomics: gradients are bit-reproducible run to run).
+// CTA = 8 producer warps (they also run the epilogue) + 1 MMA-issuing warp; 3 stages x 64 KB.
+#include "tc_common.cuh"
+
+namespace marl {
+namespace wg {
+
+using namespace tc;
+
+constexpr int BK = 32, STAGES = 3;
+constexpr int PLANE = 128 * 128;                 // [128 features x 32 rows] x 4 B
+constexpr int STAGE_BYTES = 4 * PLANE;           // A_hi, A_lo, B_hi, B_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
+constexpr int THREADS = 288;
+constexpr int MAX_KB_PER_SLICE = 64;
+
+struct Args {
+    const float *dY, *X;
+    float *partial;                              // [slices, tiles, 128, 128]
+    int64_t lddy, ldx, R, rows_per_slice;
+    int n_tiles_k;                               // K_in / 128 (tile index = n_tile * n_tiles_k + k_tile)
+};
+
+// transposed, split store of one operand: rows r0 + 4*rg + (lane >> 3), features c0 + 8*cg + (lane & 7)
+__device__ __forceinline__ void load_patch_row(const float *__restrict__ src, int64_t ld, int64_t R, int64_t row, int c0, int lane, float (&v)[16])
+{
+    const bool ok = row < R;
+    const float *p = src + row * ld + c0 + (lane & 7);
+#pragma unroll
+    for (int cg = 0; cg < 16; ++cg) v[cg] = ok ? __ldg(p + 8 * cg) : 0.f;
+}
+__device__ __forceinline__ void store_patch_row(unsigned char *hi_plane, int r, int lane, const float (&v)[16])
+{
+#pragma unroll
+    for (int cg = 0; cg < 16; ++cg) {
+        const int c = 8 * cg + (lane & 7);
+        float hi, lo;
+        split_tf32(v[cg], hi, lo);
+        const int off = c * 128 + ((((r >> 2) ^ (c & 7))) << 4) + (r & 3) * 4;
+        *reinterpret_cast<float *>(hi_plane + off) = hi;
+        *reinterpret_cast<float *>(hi_plane + PLANE + off) = lo;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+wgrad_kernel(const __grid_constant__ Args a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);     // full[3], empty[3], done
+    uint32_t *slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.y, n0 = (tile / a.n_tiles_k) * 128, k0 = (tile % a.n_tiles_k) * 128;
+    const int64_t r_begin = (int64_t)blockIdx.x * a.rows_per_slice;
+    int64_t r_end = r_begin + a.rows_per_slice;
+    if (r_end > a.R) r_end = a.R;
+    const int KB = r_end > r_begin ? (int)((r_end - r_begin + BK - 1) / BK) : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&bars[s]), 256);
+            mbar_init(smem_u32(&bars[STAGES + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *slot;
+
+    if (warp < 8) {
+        // ------------------------------------------------------------------ producers: warp w owns rows 4w .. 4w+3 of every k-block
+        const int r_in = 4 * warp + (lane >> 3);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES, round = kb / STAGES;
+            const int64_t row = r_begin + (int64_t)kb * BK + r_in;
+            float va[16], vb[16];
+            load_patch_row(a.dY, a.lddy, r_end, row, n0, lane, va);      // loads in flight while waiting for the stage
+            load_patch_row(a.X, a.ldx, r_end, row, k0, lane, vb);
+            if (round > 0) mbar_wait(smem_u32(&bars[STAGES + s]), (uint32_t)((round - 1) & 1));
+            unsigned char *st = smem + s * STAGE_BYTES;
+            store_patch_row(st, r_in, lane, va);
+            store_patch_row(st + 2 * PLANE, r_in, lane, vb);
+            fence_async_smem();
+            mbar_arrive(smem_u32(&bars[s]));
+        }
+        // ------------------------------------------------------------------ epilogue: partial tile = main0 + main1 + corr
+        mbar_wait(smem_u32(&bars[2 * STAGES]), 0);
+        fence_after();
+        const int n = 32 * (warp & 3) + lane, half = warp >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+        float *out = a.partial + (((size_t)blockIdx.x * gridDim.y + tile) * 128 + n) * 128;
+#pragma unroll 1
+        for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 16) {
+            uint32_t m0[16], m1[16], cr[16];
+            TC_TMEM_LD16(m0, taddr + (uint32_t)c0);
+            TC_TMEM_LD16(m1, taddr + (uint32_t)(128 + c0));
+            TC_TMEM_LD16(cr, taddr + (uint32_t)(256 + c0));
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                float4 o;
+                float *of = reinterpret_cast<float *>(&o);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v = KB > 0 ? __uint_as_float(m0[j + q]) : 0.f;
+                    if (KB > 1) v += __uint_as_float(m1[j + q]);
+                    if (KB > 0) v += __uint_as_float(cr[j + q]);
+                    of[q] = v;
+                }
+                *reinterpret_cast<float4 *>(out + c0 + j) = o;
+            }
+        }
+    } else if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = idesc_tf32(128, 128);
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES, round = kb / STAGES;
+            mbar_wait(smem_u32(&bars[s]), (uint32_t)(round & 1));
+            fence_after();
+            const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+            const uint64_t a_hi0 = make_desc(base), a_lo0 = make_desc(base + PLANE), b_hi0 = make_desc(base + 2 * PLANE), b_lo0 = make_desc(base + 3 * PLANE);
+            const uint32_t main_acc = tmem_base + (uint32_t)(kb & 1) * 128u, corr = tmem_base + 256u;
+#pragma unroll
+            for (int kk = 0; kk < BK / 8; ++kk) {
+                umma_tf32(main_acc, a_hi0 + 2 * kk, b_hi0 + 2 * kk, idesc, (kb >= 2 || kk) ? 1u : 0u);
+                umma_tf32(corr, a_lo0 + 2 * kk, b_hi0 + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                umma_tf32(corr, a_hi0 + 2 * kk, b_lo0 + 2 * kk, idesc, 1u);
+            }
+            umma_commit(smem_u32(&bars[STAGES + s]));
+        }
+        umma_commit(smem_u32(&bars[2 * STAGES]));
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// dW[n0+n][k0+k] (+)= sum_s partial[s][tile][n][k]   (fixed summation order: deterministic)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float *__restrict__ partial, int slices, int tiles, int n_tiles_k, float *__restrict__ dW, int64_t lddw, int accumulate)
+{
+    const int tile = blockIdx.y;
+    const int idx = blockIdx.x * 256 + threadIdx.x;          // float4 index inside the 128x128 tile
+    if (idx >= 128 * 32) return;
+    const int n = idx >> 5, k4 = (idx & 31) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < slices; ++s) {
+        const float4 v = *reinterpret_cast<const float4 *>(partial + (((size_t)s * tiles + tile) * 128 + n) * 128 + k4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float *dst = dW + (int64_t)((tile / n_tiles_k) * 128 + n) * lddw + (tile % n_tiles_k) * 128 + k4;
+    if (accumulate) { dst[0] += acc.x; dst[1] += acc.y; dst[2] += acc.z; dst[3] += acc.w; }
+    else { dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w; }
+}
+
+static int64_t slices_for(int64_t R)
+{
+    const int64_t kbs = (R + BK - 1) / BK;
+    int64_t s = (kbs + MAX_KB_PER_SLICE - 1) / MAX_KB_PER_SLICE;
+    return s < 1 ? 1 : s;
+}
+
+}  // namespace wg
+}  // namespace marl
+
+using namespace marl;
+
+extern "C" int64_t marl_wgrad_workspace_bytes(int64_t R, int32_t N_out, int32_t K_in)
+{
+    if (R <= 0 || N_out <= 0 || K_in <= 0) return -1;
+    return wg::slices_for(R) * (int64_t)(N_out / 128) * (K_in / 128) * 128 * 128 * 4;
+}
+
+extern "C" int marl_wgrad_tf32x3(int64_t R, int32_t N_out, int32_t K_in, const float *d_dY, int64_t lddy, const float *d_X, int64_t ldx,
+                                 float *d_dW, int64_t lddw, int32_t accumulate, void *d_workspace, void *stream)
+{
+    MARL_REQUIRE(R > 0 && N_out > 0 && K_in > 0 && (N_out % 128) == 0 && (K_in % 128) == 0, "marl_wgrad_tf32x3: R=%lld N_out=%d K_in=%d (need multiples of 128)",
+                 (long long)R, N_out, K_in);
+    MARL_REQUIRE(d_dY && d_X && d_dW && d_workspace && lddy >= N_out && ldx >= K_in && lddw >= K_in, "marl_wgrad_tf32x3: bad pointer / leading dimension");
+    const int64_t slices = wg::slices_for(R);
+    const int tiles = (N_out / 128) * (K_in / 128);
+    MARL_REQUIRE(slices <= 65535 * 16, "marl_wgrad_tf32x3: R too large");
+    wg::Args a;
+    a.dY = d_dY; a.X = d_X; a.partial = static_cast<float *>(d_workspace); a.lddy = lddy; a.ldx = ldx; a.R = R;
+    const int64_t kbs = (R + wg::BK - 1) / wg::BK;
+    a.rows_per_slice = ((kbs + slices - 1) / slices) * wg::BK;
+    a.n_tiles_k = K_in / 128;
+    cudaError_t e = cudaFuncSetAttribute(wg::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("wgrad_kernel: smem %d: %s", wg::SMEM_BYTES, cudaGetErrorString(e)); return MARL_ECUDA; }
+    wg::wgrad_kernel<<<dim3((unsigned)slices, (unsigned)tiles), wg::THREADS, wg::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    int rc = check_launch("wgrad_kernel");
+    if (rc) return rc;
+    wg::wgrad_reduce_kernel<<<dim3(16, (unsigned)tiles), 256, 0, (cudaStream_t)stream>>>(a.partial, (int)slices, tiles, a.n_tiles_k, d_dW, lddw, accumulate);
+    return check_launch("wgrad_reduce_kernel");
+}

@@ -79,6 +79,27 @@ def _gemm_tc(x, x2, W, bias, add, relu, out=None):
     return out
 
 
+def _wgrad_ok(dy, x):
+    return (USE_TENSOR_CORES and dy.is_cuda and dy.dtype == torch.float32 and x.dtype == torch.float32 and dy.shape[0] >= 2048
+            and dy.shape[1] % 128 == 0 and x.shape[1] % 128 == 0 and dy.stride(1) == 1 and x.stride(1) == 1)
+
+
+def wgrad(dy, x, out=None, col0=0):
+    """dW = dy^T @ x on the tensor cores (3xTF32, deterministic split-K); writes into out[:, col0 : col0 + x.shape[1]] if given."""
+    R, N = dy.shape
+    K = x.shape[1]
+    if out is None:
+        out = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+    if not _wgrad_ok(dy, x):
+        out[:, col0:col0 + K] = dy.t() @ x
+        return out
+    ws = torch.empty(int(_L().marl_wgrad_workspace_bytes(R, N, K)), dtype=torch.uint8, device=dy.device)
+    dst = out[:, col0:]
+    _lib.check(_L().marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dst.data_ptr(), out.stride(0), 0,
+                                      ws.data_ptr(), _lib.stream_ptr()), "marl_wgrad_tf32x3")
+    return out
+
+
 class _LinearTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, x2, W, bias, add, relu):
@@ -104,8 +125,13 @@ class _LinearTC(torch.autograd.Function):
         if has_x2 and need[1]:
             Wt2 = W[:, K1:].t().contiguous()
             dx2 = _gemm_tc(dy, None, Wt2, None, None, False) if _tc_ok(dy, Wt2, None) else dy @ W[:, K1:]
-        if need[2]:   # weight gradient: reduction over the (huge) row dimension, library GEMM
-            dW = torch.cat([dy.t() @ x, dy.t() @ x2], dim=1) if has_x2 else dy.t() @ x
+        if need[2]:   # weight gradient: reduction over the (huge) row dimension -> split-K tensor-core kernel
+            if has_x2:
+                dW = torch.empty(W.shape[0], W.shape[1], dtype=torch.float32, device=dy.device)
+                wgrad(dy, x, dW, 0)
+                wgrad(dy, x2, dW, K1)
+            else:
+                dW = wgrad(dy, x)
         if has_bias and need[3]:
             db = dy.sum(0)
         if has_add and need[4]:
@@ -237,7 +263,7 @@ class _GRULayer(torch.autograd.Function):
             h_prev_all = torch.cat([h0c.unsqueeze(0), out[:-1]], dim=0).view(T * R, E)
             w_ih_T = w_ih.t().contiguous()
             dx = (_gemm_tc(dgi2, None, w_ih_T, None, None, False) if _tc_ok(dgi2, w_ih_T, None) else torch.mm(dgi2, w_ih)).view(T, R, E)
-            return dx, dh0, torch.mm(dgi2.t(), x.view(T * R, E)), torch.mm(dgh2.t(), h_prev_all), dgi2.sum(0), dgh2.sum(0)
+            return dx, dh0, wgrad(dgi2, x.view(T * R, E)), wgrad(dgh2, h_prev_all), dgi2.sum(0), dgh2.sum(0)
         x, h0, w_ih, w_hh, out, saves = ctx.saved_tensors
         T, R, E = x.shape
         d_out = d_out.contiguous()

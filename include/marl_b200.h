@@ -379,6 +379,15 @@ int marl_gru_seq_fwd(int32_t T, int64_t R, int32_t E, const float *d_gi, const f
 int marl_gru_seq_bwd(int32_t T, int64_t R, int32_t E, const float *d_dout, const float *d_saves, const float *d_out,
                      const float *d_h0, const void *d_packed, float *d_dgi, float *d_dgh, float *d_dh0, void *stream);
 
+/* Weight gradient of a dense layer on the tcgen05 tensor cores (3xTF32, fp32-level accuracy, deterministic split-K):
+ * dW[n][k] (+)= sum_{r<R} dY[r][n] X[r][k], dY f32 [R, N_out] (row stride lddy), X f32 [R, K_in] (row stride ldx), dW row stride
+ * lddw (so the two halves of a concatenated input can be written into column ranges of one gradient).  Replaces the autograd
+ * weight-gradient GEMMs behind `ac_loss.backward()` (DHGN/mappo_parallel.py:708).  N_out, K_in multiples of 128.
+ * d_workspace: marl_wgrad_workspace_bytes(R, N_out, K_in) bytes. */
+int64_t marl_wgrad_workspace_bytes(int64_t R, int32_t N_out, int32_t K_in);
+int marl_wgrad_tf32x3(int64_t R, int32_t N_out, int32_t K_in, const float *d_dY, int64_t lddy, const float *d_X, int64_t ldx,
+                      float *d_dW, int64_t lddw, int32_t accumulate, void *d_workspace, void *stream);
+
 /* torch.nn.utils.clip_grad_norm_ (:710-711) and torch.optim.Adam.step (runner.py:72-78) on flat fp32 arenas. */
 int64_t marl_clip_workspace_bytes(int64_t n);
 int marl_clip_grad_norm(int64_t n, float *d_grad, float max_norm, void *d_workspace, float *d_total_norm, void *stream);

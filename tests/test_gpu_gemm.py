@@ -84,3 +84,34 @@ def test_gemm_throughput_note():
         e.synchronize()
         ms = s.elapsed_time(e) / 20
         print(f"{name}: {ms * 1e3:.1f} us  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+
+
+@pytest.mark.parametrize("R,N,K,ldx_extra", [(5000, 128, 128, 0), (2048, 384, 128, 0), (70001, 128, 256, 4), (33, 128, 128, 0), (4097, 256, 384, 0)])
+def test_wgrad_tf32x3_matches_fp64(R, N, K, ldx_extra):
+    """dW = dY^T X (split-K tensor-core kernel) against an fp64 reference; also deterministic run to run."""
+    import ctypes
+    from distributed_multi_agent_reinforcement_learning_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(R + N)
+    dy = torch.randn(R, N, device="cuda", generator=g)
+    xfull = torch.randn(R, K + ldx_extra, device="cuda", generator=g)
+    x = xfull[:, :K]
+    ref = (dy.double().t() @ x.double())
+    ws = torch.empty(int(L.marl_wgrad_workspace_bytes(R, N, K)), dtype=torch.uint8, device="cuda")
+    outs = []
+    for _ in range(2):
+        dW = torch.full((N, K + 8), 7.0, device="cuda")
+        _lib.check(L.marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dW.data_ptr(), dW.stride(0), 0,
+                                       ws.data_ptr(), _lib.stream_ptr()), "marl_wgrad_tf32x3")
+        torch.cuda.synchronize()
+        outs.append(dW.clone())
+    assert torch.equal(outs[0], outs[1])
+    assert (outs[0][:, K:] == 7.0).all()                       # nothing written outside the tile columns
+    err = (outs[0][:, :K].double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    fp32 = ((dy.t() @ x).double() - ref).abs().max().item()    # what the library sgemm achieves
+    assert err <= max(5e-6 * scale, 4.0 * fp32), (err, fp32, scale)      # fp32-level: a few ulp of the accumulated magnitude
+    # accumulate mode
+    _lib.check(L.marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dW.data_ptr(), dW.stride(0), 1,
+                                   ws.data_ptr(), _lib.stream_ptr()), "marl_wgrad_tf32x3")
+    torch.testing.assert_close(dW[:, :K], 2 * outs[0][:, :K], rtol=1e-6, atol=1e-6 * scale)
