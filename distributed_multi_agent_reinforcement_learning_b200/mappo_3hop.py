@@ -236,7 +236,7 @@ class MAPPO:
         self.ac_optimizer.zero_grad()
         E, L = self.rnn_hidden_dim, self.num_layers
         cm = self.critic.Mean
-        with torch.enable_grad():
+        with torch.enable_grad(), ops.pack_scope():
             for num, batch, T, adv, v_target in per_team:
                 for lo in range(0, self.batch_size, self.mini_batch_size):
                     idx = slice(lo, min(lo + self.mini_batch_size, self.batch_size))

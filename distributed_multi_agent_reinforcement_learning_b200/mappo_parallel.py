@@ -433,7 +433,7 @@ class MAPPO:
         mbs = self.mini_batch_size or bs
         obj_c = obj_a = 0.0
         n_updates = 0
-        with torch.enable_grad():
+        with torch.enable_grad(), ops.pack_scope():       # weights are fixed for the whole epoch: pack them once
             for lo in range(0, bs, mbs):
                 hi = min(lo + mbs, bs)
                 mb = tb.minibatch(lo, hi)

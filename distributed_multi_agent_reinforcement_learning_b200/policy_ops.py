@@ -60,17 +60,84 @@ def _tc_ok(x, W, x2):
             and (K - K1) % 32 == 0 and W.stride(1) == 1 and W.stride(0) % 4 == 0 and W.data_ptr() % 16 == 0)
 
 
-def _gemm_tc(x, x2, W, bias, add, relu, out=None):
-    """C = act(x W[:, :K1]^T + x2 W[:, K1:]^T + bias + add) through marl_gemm_tf32x3."""
+USE_ROWGEMM = True          # persistent row-tile kernel (csrc/rowgemm_tf32x3.cu) when N, K1, K2 are multiples of 128
+_PACK_CACHE = {}
+_PACK_SCOPE = [0]
+
+
+class pack_scope:
+    """Within the scope, packed (hi/lo split, swizzled) weight images are cached per weight view: the weights must not change
+    inside it (MAPPO.train: one optimizer step per epoch, after all minibatches)."""
+
+    def __enter__(self):
+        _PACK_SCOPE[0] += 1
+        return self
+
+    def __exit__(self, *exc):
+        _PACK_SCOPE[0] -= 1
+        if _PACK_SCOPE[0] == 0:
+            _PACK_CACHE.clear()
+        return False
+
+
+def _packed_weight(W, N, K, stride_n, stride_k):
+    """Packed image of B[n][k] = W.data[n*stride_n + k*stride_k] (n < N, k < K)."""
+    key = (W.data_ptr(), N, K, stride_n, stride_k)
+    if _PACK_SCOPE[0] and key in _PACK_CACHE:
+        return _PACK_CACHE[key]
+    nbytes = int(_L().marl_rowgemm_pack_bytes(N, K))
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=W.device)
+    off = (-buf.data_ptr()) % 1024
+    packed = buf[off:off + nbytes]
+    _lib.check(_L().marl_rowgemm_pack(W.data_ptr(), stride_n, stride_k, N, K, packed.data_ptr(), _lib.stream_ptr()), "marl_rowgemm_pack")
+    if _PACK_SCOPE[0]:
+        _PACK_CACHE[key] = packed
+    return packed
+
+
+def _rowgemm_ok(M, N, K1, K2):
+    return USE_ROWGEMM and N % 128 == 0 and N <= 512 and K1 % 128 == 0 and K2 % 128 == 0 and M >= 256
+
+
+def _aligned_rows(t):
+    return t if (t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0) else t.contiguous()
+
+
+def _tc_t_ok(dy, Wslice):
+    """dX = dY Wslice on the tensor cores: reduction over Wslice.shape[0] (must equal dy.shape[1]), output width Wslice.shape[1]."""
+    N, K = Wslice.shape
+    return (USE_TENSOR_CORES and dy.is_cuda and dy.dtype == torch.float32 and K % 128 == 0 and N % 32 == 0 and Wslice.stride(1) == 1
+            and Wslice.data_ptr() % 16 == 0 and Wslice.stride(0) % 4 == 0)
+
+
+def _gemm_tc(x, x2, W, bias, add, relu, out=None, transposed=False):
+    """C = act(x B[:, :K1]^T + x2 B[:, K1:]^T + bias + add), B = W (nn.Linear weight [N,K]) or, with transposed=True, W^T
+    (then W is [K, N]: dX = dY W without materialising the transpose)."""
     M, K1 = x.shape
-    N, K = W.shape
-    x = x if (x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0) else x.contiguous()
+    if transposed:
+        K, N = W.shape
+        stride_n, stride_k = W.stride(1), W.stride(0)
+    else:
+        N, K = W.shape
+        stride_n, stride_k = W.stride(0), W.stride(1)
+    K2 = K - K1
+    x = _aligned_rows(x)
     if x2 is not None:
-        x2 = x2 if (x2.stride(1) == 1 and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0) else x2.contiguous()
+        x2 = _aligned_rows(x2)
     if add is not None:
-        add = add if (add.stride(1) == 1 and add.stride(0) % 4 == 0 and add.data_ptr() % 16 == 0) else add.contiguous()
+        add = _aligned_rows(add)
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    if _rowgemm_ok(M, N, K1, K2):
+        packed = _packed_weight(W, N, K, stride_n, stride_k)
+        _lib.check(_L().marl_rowgemm_tf32x3(
+            M, N, K1, K2, x.data_ptr(), x.stride(0), x2.data_ptr() if x2 is not None else None, x2.stride(0) if x2 is not None else 0,
+            packed.data_ptr(), bias.data_ptr() if bias is not None else None, add.data_ptr() if add is not None else None,
+            add.stride(0) if add is not None else 0, out.data_ptr(), out.stride(0), 1 if relu else 0, _lib.stream_ptr()),
+            "marl_rowgemm_tf32x3")
+        return out
+    if transposed:
+        W = W.t().contiguous()
     _lib.check(_L().marl_gemm_tf32x3(
         M, N, K1, K - K1, x.data_ptr(), x.stride(0), x2.data_ptr() if x2 is not None else None,
         x2.stride(0) if x2 is not None else 0, W.data_ptr(), W.stride(0), bias.data_ptr() if bias is not None else None,
@@ -119,12 +186,10 @@ class _LinearTC(torch.autograd.Function):
         K1 = x.shape[1]
         need = ctx.needs_input_grad
         dx = dx2 = dW = db = dadd = None
-        if need[0]:   # dX = dY W[:, :K1]: same kernel with the transposed weight slice as "W"
-            Wt = W[:, :K1].t().contiguous()
-            dx = _gemm_tc(dy, None, Wt, None, None, False) if _tc_ok(dy, Wt, None) else dy @ W[:, :K1]
+        if need[0]:   # dX = dY W[:, :K1]: same kernel, the weight slice packed through its transposed view
+            dx = _gemm_tc(dy, None, W[:, :K1], None, None, False, transposed=True) if _tc_t_ok(dy, W[:, :K1]) else dy @ W[:, :K1]
         if has_x2 and need[1]:
-            Wt2 = W[:, K1:].t().contiguous()
-            dx2 = _gemm_tc(dy, None, Wt2, None, None, False) if _tc_ok(dy, Wt2, None) else dy @ W[:, K1:]
+            dx2 = _gemm_tc(dy, None, W[:, K1:], None, None, False, transposed=True) if _tc_t_ok(dy, W[:, K1:]) else dy @ W[:, K1:]
         if need[2]:   # weight gradient: reduction over the (huge) row dimension -> split-K tensor-core kernel
             if has_x2:
                 dW = torch.empty(W.shape[0], W.shape[1], dtype=torch.float32, device=dy.device)
@@ -261,8 +326,7 @@ class _GRULayer(torch.autograd.Function):
                        "marl_gru_seq_bwd")
             dgi2, dgh2 = dgi.view(T * R, 3 * E), dgh.view(T * R, 3 * E)
             h_prev_all = torch.cat([h0c.unsqueeze(0), out[:-1]], dim=0).view(T * R, E)
-            w_ih_T = w_ih.t().contiguous()
-            dx = (_gemm_tc(dgi2, None, w_ih_T, None, None, False) if _tc_ok(dgi2, w_ih_T, None) else torch.mm(dgi2, w_ih)).view(T, R, E)
+            dx = (_gemm_tc(dgi2, None, w_ih, None, None, False, transposed=True) if _tc_t_ok(dgi2, w_ih) else torch.mm(dgi2, w_ih)).view(T, R, E)
             return dx, dh0, wgrad(dgi2, x.view(T * R, E)), wgrad(dgh2, h_prev_all), dgi2.sum(0), dgh2.sum(0)
         x, h0, w_ih, w_hh, out, saves = ctx.saved_tensors
         T, R, E = x.shape

@@ -388,6 +388,16 @@ int64_t marl_wgrad_workspace_bytes(int64_t R, int32_t N_out, int32_t K_in);
 int marl_wgrad_tf32x3(int64_t R, int32_t N_out, int32_t K_in, const float *d_dY, int64_t lddy, const float *d_X, int64_t ldx,
                       float *d_dW, int64_t lddw, int32_t accumulate, void *d_workspace, void *stream);
 
+/* Persistent row-tile GEMM for training (forward and input-gradient GEMMs of every E-wide layer), tcgen05 3xTF32:
+ * C[M,N] = act([A1 | A2] B^T + bias + D), B[N, K1+K2] given pre-packed by marl_rowgemm_pack from any strided view
+ * (B[n][k] = d_W[n*stride_n + k*stride_k]: an nn.Linear weight as is, or its transpose for dX = dY W).  N <= 512 and all of
+ * N, K1, K2 multiples of 128 (K2 may be 0); rows 16-byte aligned.  d_packed: 1024-byte aligned, marl_rowgemm_pack_bytes(N, K). */
+int64_t marl_rowgemm_pack_bytes(int32_t N, int32_t K);
+int marl_rowgemm_pack(const float *d_W, int64_t stride_n, int64_t stride_k, int32_t N, int32_t K, void *d_packed, void *stream);
+int marl_rowgemm_tf32x3(int64_t M, int32_t N, int32_t K1, int32_t K2, const float *d_A1, int64_t lda1, const float *d_A2, int64_t lda2,
+                        const void *d_packed, const float *d_bias, const float *d_D, int64_t ldd, float *d_C, int64_t ldc, int32_t relu,
+                        void *stream);
+
 /* torch.nn.utils.clip_grad_norm_ (:710-711) and torch.optim.Adam.step (runner.py:72-78) on flat fp32 arenas. */
 int64_t marl_clip_workspace_bytes(int64_t n);
 int marl_clip_grad_norm(int64_t n, float *d_grad, float max_norm, void *d_workspace, float *d_total_norm, void *stream);

@@ -54,6 +54,8 @@ def test_linear_autograd_matches_library():
     M, E = 2050, 128
     mk = lambda *s: torch.randn(*s, device="cuda", generator=g)
     x, x2, W, b, add = mk(M, E), mk(M, E), mk(E, 2 * E) * 0.1, mk(E) * 0.1, mk(M, E)
+    pre = torch.addmm(b, torch.cat([x, x2], 1), W.t()) + add
+    add = add + (pre.abs() < 1e-3) * 1e-2        # keep every pre-activation away from the ReLU knife edge (mask parity)
     a = [t.clone().requires_grad_(True) for t in (x, x2, W, b, add)]
     out = ops.linear(a[0], a[2], a[3], True, x2=a[1], add=a[4])
     r = [t.clone().requires_grad_(True) for t in (x, x2, W, b, add)]
@@ -115,3 +117,36 @@ def test_wgrad_tf32x3_matches_fp64(R, N, K, ldx_extra):
     _lib.check(L.marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dW.data_ptr(), dW.stride(0), 1,
                                    ws.data_ptr(), _lib.stream_ptr()), "marl_wgrad_tf32x3")
     torch.testing.assert_close(dW[:, :K], 2 * outs[0][:, :K], rtol=1e-6, atol=1e-6 * scale)
+
+
+@pytest.mark.parametrize("M,N,K1,K2,relu,use_add", [(1000, 128, 128, 0, True, False), (4097, 384, 128, 0, False, False), (333, 128, 128, 128, True, False),
+                                                    (70000, 128, 384, 0, False, True), (260, 512, 256, 0, True, True)])
+def test_rowgemm_matches_fp64(M, N, K1, K2, relu, use_add):
+    """Persistent row-tile GEMM (csrc/rowgemm_tf32x3.cu) through policy_ops.linear, forward and both gradients, vs fp64."""
+    from distributed_multi_agent_reinforcement_learning_b200 import policy_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(M)
+    mk = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    x, x2 = mk(M, K1).requires_grad_(True), (mk(M, K2).requires_grad_(True) if K2 else None)
+    W, b = (mk(N, K1 + K2) / 8).requires_grad_(True), mk(N).requires_grad_(True)
+    add = mk(M, N) if use_add else None
+    if relu:                                      # keep pre-activations away from the ReLU knife edge (mask parity in backward)
+        xin0 = x.detach() if x2 is None else torch.cat([x.detach(), x2.detach()], 1)
+        pre = torch.addmm(b.detach(), xin0, W.detach().t()) + (add if add is not None else 0)
+        fix = (pre.abs() < 1e-3) * 1e-2
+        add = fix if add is None else add + fix
+    assert ops._rowgemm_ok(M, N, K1, K2)
+    out = ops.linear(x, W, b, relu=relu, x2=x2, add=add)
+    xin = x.double() if x2 is None else torch.cat([x.double(), x2.double()], 1)
+    ref = xin @ W.double().t() + b.double() + (add.double() if add is not None else 0)
+    ref = torch.relu(ref) if relu else ref
+    scale = ref.abs().max().item()
+    assert (out.double() - ref).abs().max().item() <= 4e-6 * scale      # 3-4 output tiles share one accumulator per tile
+    dout = mk(M, N)
+    out.backward(dout)
+    gx, gW, gb = x.grad.clone(), W.grad.clone(), b.grad.clone()
+    gx2 = x2.grad.clone() if x2 is not None else None
+    for t in (x, W, b) + ((x2,) if x2 is not None else ()):
+        t.grad = None
+    ref.backward(dout.double())
+    for mine, theirs in ((gx, x.grad), (gW, W.grad), (gb, b.grad)) + (((gx2, x2.grad),) if x2 is not None else ()):
+        assert (mine.double() - theirs.double()).abs().max().item() <= 5e-6 * theirs.abs().max().item() + 1e-7
