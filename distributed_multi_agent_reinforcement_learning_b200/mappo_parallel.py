@@ -28,6 +28,9 @@ from .normalization import Normalization
 from .replay_buffer import BigBuffer, ReplayBuffer
 
 
+TWO_STREAM_TRAIN = True     # actor and critic branches of a training minibatch on two CUDA streams
+
+
 def orthogonal_init(layer, gain=1.0):
     for name, param in layer.named_parameters():
         if "bias" in name:
@@ -389,10 +392,27 @@ class MAPPO:
         graph = mb.graph()
         enc = self.actor.shared_net
         h0 = torch.zeros(self.num_layers, B * N, E, dtype=torch.float32, device=self.device)
-        emb_a = enc.encode(graph, False, mb.history("actor"))
-        feat_a, _ = self.actor.features(emb_a.view(T, B * N, E), h0)
-        emb_c = enc.encode(graph, True, mb.history("critic"))
-        feat_c, _ = self.critic.features(emb_c.view(T, B * N, E), h0)
+        # The two networks are independent until the loss: the critic branch runs on a side stream, concurrently with the actor
+        # branch (forward here, and backward too: autograd replays each node on the stream of its forward).  The GRU sequence
+        # kernels of a minibatch only fill 50-100 of the 148 SMs, so the pair overlaps almost perfectly.
+        main = torch.cuda.current_stream()
+        if TWO_STREAM_TRAIN and not torch.cuda.is_current_stream_capturing():
+            if getattr(self, "_critic_stream", None) is None:
+                self._critic_stream = torch.cuda.Stream(device=self.device)
+            side = self._critic_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                emb_c = enc.encode(graph, True, mb.history("critic"))
+                feat_c, _ = self.critic.features(emb_c.view(T, B * N, E), h0)
+            emb_a = enc.encode(graph, False, mb.history("actor"))
+            feat_a, _ = self.actor.features(emb_a.view(T, B * N, E), h0)
+            main.wait_stream(side)
+            feat_c.record_stream(main)
+        else:
+            emb_a = enc.encode(graph, False, mb.history("actor"))
+            feat_a, _ = self.actor.features(emb_a.view(T, B * N, E), h0)
+            emb_c = enc.encode(graph, True, mb.history("critic"))
+            feat_c, _ = self.critic.features(emb_c.view(T, B * N, E), h0)
         cm = self.critic.Mean
         R = T * B * N
         flat = lambda x: x.reshape(R)

@@ -82,7 +82,7 @@ class pack_scope:
 
 def _packed_weight(W, N, K, stride_n, stride_k):
     """Packed image of B[n][k] = W.data[n*stride_n + k*stride_k] (n < N, k < K)."""
-    key = (W.data_ptr(), N, K, stride_n, stride_k)
+    key = (W.data_ptr(), N, K, stride_n, stride_k, torch.cuda.current_stream().cuda_stream)   # packed on the stream that uses it
     if _PACK_SCOPE[0] and key in _PACK_CACHE:
         return _PACK_CACHE[key]
     nbytes = int(_L().marl_rowgemm_pack_bytes(N, K))
