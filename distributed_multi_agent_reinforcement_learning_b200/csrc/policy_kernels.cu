@@ -10,6 +10,7 @@
 // One warp per (sample, agent) row; lane l owns channels l, l+32, ... (E = 32*CPL), so every [.,E] access is a
 // coalesced 128-byte line per CPL.
 #include "common.cuh"
+#include "msg_args.cuh"
 #include <type_traits>
 
 namespace marl {
@@ -34,18 +35,7 @@ struct MsgWeights {   // per-lane slices of MSG_layers.{0,1,2} (weights [E,8], [
     }
 };
 
-struct MsgArgs {
-    int S, N, O, NW, OW;
-    const float *p;            // [S,N,4]
-    const float *e;            // [S,4]
-    const float *oxy;          // [Bo,O,2] obstacle-cell coordinates (vx=vy=0 implied, pursuit_env.py:22-26)
-    const int32_t *o_index;    // [S] row of oxy for this sample
-    const int32_t *o_count;    // [Bo] slots that exist for all-ones adjacency (critic): O_b in rollout, O in training
-    const uint32_t *p_adj;     // [S,N,NW] or null when all_ones
-    const uint8_t *e_adj;      // [S,N]
-    const uint32_t *o_adj;     // [S,N,OW]
-    int all_ones;              // critic: AttributeDataset(is_critic=True) (mappo_parallel.py:64-65)
-};
+
 
 // torch's F.linear accumulates k = 0..K-1 in order; keep that order (fp32 sums are order sensitive)
 __device__ __forceinline__ float dot4(const float (&w)[4], float a0, float a1, float a2, float a3, float b)
@@ -597,6 +587,7 @@ extern "C" int marl_dhgn_message_fwd(MSG_ARGS_DECL, const float *d_W0, const flo
     int rc = fill_msg_args(a, S, N, O, E, d_p, d_e, d_oxy, d_o_index, d_o_count, d_p_adj_bits, d_e_adj, d_o_adj_bits, all_ones);
     if (rc) return rc;
     MARL_REQUIRE(d_W0 && d_b0 && d_W1 && d_b1 && d_W2 && d_b2 && d_agg, "marl_dhgn_message_fwd: null pointer");
+    if (msg_grouped_supported(a, E)) return launch_msg_fwd_grouped(a, d_W0, d_b0, d_W1, d_b1, d_W2, d_b2, d_agg, (cudaStream_t)stream);
     return dispatch_cpl(E, [&](auto C_) -> int {
         constexpr int CPL = decltype(C_)::value;
         msg_agg_fwd_kernel<CPL><<<grid_for_rows((int64_t)S * N), kPolThreads, 0, (cudaStream_t)stream>>>(
@@ -615,6 +606,8 @@ extern "C" int marl_dhgn_message_bwd(MSG_ARGS_DECL, const float *d_W0, const flo
     if (rc) return rc;
     MARL_REQUIRE(d_W0 && d_b0 && d_W1 && d_b1 && d_W2 && d_b2 && d_grad_agg && d_gW0 && d_gb0 && d_gW1 && d_gb1 && d_gW2 && d_gb2,
                  "marl_dhgn_message_bwd: null pointer");
+    if (msg_grouped_supported(a, E))
+        return launch_msg_bwd_grouped(a, d_W0, d_b0, d_W1, d_b1, d_W2, d_b2, d_grad_agg, d_gW0, d_gb0, d_gW1, d_gb1, d_gW2, d_gb2, (cudaStream_t)stream);
     return dispatch_cpl(E, [&](auto C_) -> int {
         constexpr int CPL = decltype(C_)::value;
         int blocks = grid_for_rows((int64_t)S * N);
