@@ -427,3 +427,29 @@ def test_explore_env_reference_signature():
     learner.critic.set_weights(worker.critic.get_weights())
     objC, objA, ag, cg = learner.train(big, 2 * T)
     assert np.isfinite(objC) and np.isfinite(objA) and len(ag) == len(list(learner.actor.parameters()))
+
+
+def test_checkpoint_file_set_round_trip(tmp_path):
+    """The reference driver's eight-file checkpoint set (main.py:149-169) + recorder.npy, written and read back."""
+    from distributed_multi_agent_reinforcement_learning_b200 import checkpoint
+    from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
+    cfg = _cfg(1, 4, 5, 32)
+    torch.manual_seed(1)
+    a = MAPPO(cfg, None, None, "Worker")
+    checkpoint.save_checkpoint(a, str(tmp_path), recorder=[(10, 1.0, 0.5, 0.9, 0.1, -0.1)])
+    checkpoint.save_checkpoint(a, str(tmp_path), final=True)
+    names = sorted(os.listdir(tmp_path))
+    for n in checkpoint.FILES:
+        assert f"{n}.pth" in names and f"{n}_final.pth" in names and f"{n}.state_dict.pth" in names
+    assert np.load(os.path.join(tmp_path, "recorder.npy")).shape == (1, 6)
+    torch.manual_seed(2)
+    b = MAPPO(cfg, None, None, "Worker")
+    assert not torch.equal(a.actor.GRU.weight_hh_l0, b.actor.GRU.weight_hh_l0)
+    assert sorted(checkpoint.load_checkpoint(b, str(tmp_path))) == sorted(checkpoint.FILES)
+    for (k, u), (_, v) in zip(a.actor.state_dict().items(), b.actor.state_dict().items()):
+        assert torch.equal(u, v), k
+    for (k, u), (_, v) in zip(a.critic.state_dict().items(), b.critic.state_dict().items()):
+        assert torch.equal(u, v), k
+    # pickled whole module, as evaluator.py:329-330 consumes it
+    sd = torch.load(os.path.join(tmp_path, "actor.pth"), weights_only=False).state_dict()
+    assert list(sd.keys()) == list(a.actor.state_dict().keys())

@@ -154,3 +154,28 @@ def test_dilate_matches_oracle(oracle):
     p = oracle.EnvParams.from_fixture(fx)
     for e in (0, 1, 2, 3):
         assert np.array_equal(maps.dilate(fx["grid"], e), oracle.dilate(p, fx["grid"], e))
+
+
+def test_reference_part_checkpoints_load_into_our_modules():
+    """The reference ships model/actor_gru.pth, critic_gru.pth, actor_mean.pth, critic_mean.pth (pickled torch modules,
+    loadable without omegaconf): their state_dicts must fit the sub-modules of our classes key for key."""
+    import os
+    import pytest
+    torch = pytest.importorskip("torch")
+    ref = "/root/reference/model"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present (GPU box)")
+    import torch.nn as nn
+    from distributed_multi_agent_reinforcement_learning_b200 import checkpoint
+    from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import preproc_layer
+    gru = nn.GRU(128, 128, 2)
+    for name in ("actor_gru", "critic_gru"):
+        sd = checkpoint.load_state(os.path.join(ref, name + ".pth"))
+        assert list(sd.keys()) == list(gru.state_dict().keys())
+        gru.load_state_dict(sd)
+    sd = checkpoint.load_state(os.path.join(ref, "actor_mean.pth"))
+    head = nn.Linear(sd["weight"].shape[1], sd["weight"].shape[0]) if "weight" in sd else preproc_layer(128, 9, is_sn=True)
+    head.load_state_dict(sd)
+    sd = checkpoint.load_state(os.path.join(ref, "critic_mean.pth"))
+    critic_head = preproc_layer(128, 1, is_sn=True) if "weight_orig" in sd else nn.Linear(128, 1)
+    critic_head.load_state_dict(sd)
