@@ -84,6 +84,8 @@ rowgemm_kernel(const __grid_constant__ Args a)
     if (warp < 8) {
         // ================================================================================= workers
         int group = 0;
+        float4 nxt[16];
+        bool have_next = false;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             const int64_t row0 = (int64_t)tile * ROWS;
             for (int kc = 0; kc < a.KC; ++kc) {
@@ -91,10 +93,15 @@ rowgemm_kernel(const __grid_constant__ Args a)
                 const float *src = kc < a.KC1 ? a.A1 + kc * 128 : a.A2 + (kc - a.KC1) * 128;
                 const int64_t ld = kc < a.KC1 ? a.lda1 : a.lda2;
                 float4 v[16];
+                if (kc == 0 && have_next) {                     // chunk 0 of this tile was prefetched during the previous epilogue
 #pragma unroll
-                for (int rr = 0; rr < 16; ++rr) {
-                    const int64_t row = row0 + 16 * warp + rr;
-                    v[rr] = row < a.M ? __ldg(reinterpret_cast<const float4 *>(src + row * ld) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int rr = 0; rr < 16; ++rr) v[rr] = nxt[rr];
+                } else {
+#pragma unroll
+                    for (int rr = 0; rr < 16; ++rr) {
+                        const int64_t row = row0 + 16 * warp + rr;
+                        v[rr] = row < a.M ? __ldg(reinterpret_cast<const float4 *>(src + row * ld) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
                 if (kc > 0) {                                   // X is still being read by the previous chunk's MMAs
                     mbar_wait(smem_u32(&bars[BAR_MMA_DONE]), (uint32_t)((group - 1) & 1));
@@ -106,6 +113,16 @@ rowgemm_kernel(const __grid_constant__ Args a)
                 fence_before();
                 mbar_arrive(smem_u32(&bars[BAR_A_READY]));
                 ++group;
+            }
+            // prefetch chunk 0 of the next tile: its HBM latency hides behind this tile's MMAs and epilogue
+            have_next = tile + (int)gridDim.x < a.n_tiles;
+            if (have_next) {
+                const int64_t nrow0 = (int64_t)(tile + gridDim.x) * ROWS;
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr) {
+                    const int64_t row = nrow0 + 16 * warp + rr;
+                    nxt[rr] = row < a.M ? __ldg(reinterpret_cast<const float4 *>(a.A1 + row * a.lda1) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
             mbar_wait(smem_u32(&bars[BAR_MMA_DONE]), (uint32_t)((group - 1) & 1));
             fence_after();

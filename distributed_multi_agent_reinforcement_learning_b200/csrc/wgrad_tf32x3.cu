@@ -68,7 +68,7 @@ wgrad_kernel(const __grid_constant__ Args a)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(smem_u32(&bars[s]), 256);
+            mbar_init(smem_u32(&bars[s]), 8);
             mbar_init(smem_u32(&bars[STAGES + s]), 1);
         }
         mbar_init(smem_u32(&bars[2 * STAGES]), 1);
@@ -86,18 +86,32 @@ wgrad_kernel(const __grid_constant__ Args a)
     if (warp < 8) {
         // ------------------------------------------------------------------ producers: warp w owns rows 4w .. 4w+3 of every k-block
         const int r_in = 4 * warp + (lane >> 3);
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % STAGES, round = kb / STAGES;
+        // software pipeline: the global loads of k-block kb+1 are in flight while k-block kb is split and stored (the HBM latency
+        // of a 32-row block would otherwise be exposed once per k-block: the producers are the same threads that wait for the stage)
+        float va[16], vb[16], na[16], nb[16];
+        auto fetch = [&](int kb, float (&ua)[16], float (&ub)[16]) {
             const int64_t row = r_begin + (int64_t)kb * BK + r_in;
-            float va[16], vb[16];
-            load_patch_row(a.dY, a.lddy, r_end, row, n0, lane, va);      // loads in flight while waiting for the stage
-            load_patch_row(a.X, a.ldx, r_end, row, k0, lane, vb);
+            load_patch_row(a.dY, a.lddy, r_end, row, n0, lane, ua);
+            load_patch_row(a.X, a.ldx, r_end, row, k0, lane, ub);
+        };
+        auto publish = [&](int kb, const float (&ua)[16], const float (&ub)[16]) {
+            const int s = kb % STAGES, round = kb / STAGES;
             if (round > 0) mbar_wait(smem_u32(&bars[STAGES + s]), (uint32_t)((round - 1) & 1));
             unsigned char *st = smem + s * STAGE_BYTES;
-            store_patch_row(st, r_in, lane, va);
-            store_patch_row(st + 2 * PLANE, r_in, lane, vb);
+            store_patch_row(st, r_in, lane, ua);
+            store_patch_row(st + 2 * PLANE, r_in, lane, ub);
             fence_async_smem();
-            mbar_arrive(smem_u32(&bars[s]));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[s]));       // one arrival per warp (the fence above is per thread)
+        };
+        if (KB > 0) fetch(0, va, vb);
+        for (int kb = 0; kb < KB; kb += 2) {                    // two register sets, no copies: loads stay in flight across a whole iteration
+            if (kb + 1 < KB) fetch(kb + 1, na, nb);
+            publish(kb, va, vb);
+            if (kb + 1 < KB) {
+                if (kb + 2 < KB) fetch(kb + 2, va, vb);
+                publish(kb + 1, na, nb);
+            }
         }
         // ------------------------------------------------------------------ epilogue: partial tile = main0 + main1 + corr
         mbar_wait(smem_u32(&bars[2 * STAGES]), 0);
