@@ -175,36 +175,35 @@ gru_seq_fwd_kernel(const __grid_constant__ FwdArgs a)
         fence_before();
         mbar_arrive(smem_u32(&bars[A_READY]));
         const int64_t TRE = (int64_t)a.T * a.R * E;
+        static_assert(HALF == 16, "one x16 chunk per thread and step (the gi prefetch below holds 48 registers)");
         for (int t = 0; t < a.T; ++t) {
-            mbar_wait(smem_u32(&bars[MMA_DONE]), (uint32_t)(t & 1));
-            fence_after();
+            // this step's input projections do not depend on the MMAs: their HBM latency hides behind the wait for gh
             const float *__restrict__ gi_t = a.gi + (int64_t)t * a.R * 3 * E;
             const int64_t o_t = (int64_t)t * a.R * E;
-#pragma unroll 1
-            for (int c0 = 0; c0 < HALF; c0 += 16) {
-                // all global loads of the chunk first: the stores below may alias them as far as the compiler knows, and
-                // one exposed HBM latency per chunk instead of one per element is the difference between 43 K and 8 K cycles
-                float gir[16], giz[16], gin[16];
+            float gir[16], giz[16], gin[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int64_t row = row0 + half * HALF + c0 + j;
-                    gir[j] = giz[j] = gin[j] = 0.f;
-                    if (row < a.R) {
-                        const float *g = gi_t + row * 3 * E + f;
-                        gir[j] = __ldg(g); giz[j] = __ldg(g + E); gin[j] = __ldg(g + 2 * E);
-                    }
+            for (int j = 0; j < 16; ++j) {
+                const int64_t row = row0 + half * HALF + j;
+                gir[j] = giz[j] = gin[j] = 0.f;
+                if (row < a.R) {
+                    const float *g = gi_t + row * 3 * E + f;
+                    gir[j] = __ldg(g); giz[j] = __ldg(g + E); gin[j] = __ldg(g + 2 * E);
                 }
+            }
+            mbar_wait(smem_u32(&bars[MMA_DONE]), (uint32_t)(t & 1));
+            fence_after();
+            {
                 uint32_t ar[16], az[16], ahn[16], cr[16], cz[16], chn[16];
-                TC_TMEM_LD16(ar, taddr + (uint32_t)c0);
-                TC_TMEM_LD16(az, taddr + (uint32_t)(NR + c0));
-                TC_TMEM_LD16(ahn, taddr + (uint32_t)(2 * NR + c0));
-                TC_TMEM_LD16(cr, taddr + (uint32_t)(3 * NR + c0));
-                TC_TMEM_LD16(cz, taddr + (uint32_t)(4 * NR + c0));
-                TC_TMEM_LD16(chn, taddr + (uint32_t)(5 * NR + c0));
+                TC_TMEM_LD16(ar, taddr);
+                TC_TMEM_LD16(az, taddr + (uint32_t)NR);
+                TC_TMEM_LD16(ahn, taddr + (uint32_t)(2 * NR));
+                TC_TMEM_LD16(cr, taddr + (uint32_t)(3 * NR));
+                TC_TMEM_LD16(cz, taddr + (uint32_t)(4 * NR));
+                TC_TMEM_LD16(chn, taddr + (uint32_t)(5 * NR));
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int n = half * HALF + c0 + j;
+                    const int n = half * HALF + j;
                     const int64_t row = row0 + n;
                     const float hp = TL::load(X, n, f);
                     // ex2-based exp and the fast reciprocal: ~40 instructions per element instead of ~210 with expf / tanhf / IEEE
@@ -266,6 +265,22 @@ gru_seq_bwd_kernel(const __grid_constant__ BwdArgs a)
         for (int j = 0; j < HALF; ++j) dhz[j] = 0.f;
         for (int tt = 0; tt < a.T; ++tt) {
             const int t = a.T - 1 - tt;
+            const int64_t o_t = (int64_t)t * a.R * E;
+            const float *hprev = t > 0 ? a.out + (int64_t)(t - 1) * a.R * E : a.h0;
+            // everything this step reads from HBM is independent of the pending MMAs: issue it all before waiting for them
+            float v_do[HALF], v_r[HALF], v_z[HALF], v_n[HALF], v_hn[HALF], v_hp[HALF];
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) {
+                const int64_t row = row0 + half * HALF + j;
+                v_do[j] = v_r[j] = v_z[j] = v_n[j] = v_hn[j] = v_hp[j] = 0.f;
+                if (row < a.R) {
+                    const int64_t idx = o_t + row * E + f;
+                    v_do[j] = __ldg(a.dout + idx);
+                    v_r[j] = __ldg(a.saves + idx); v_z[j] = __ldg(a.saves + TRE + idx);
+                    v_n[j] = __ldg(a.saves + 2 * TRE + idx); v_hn[j] = __ldg(a.saves + 3 * TRE + idx);
+                    v_hp[j] = __ldg(hprev + row * E + f);
+                }
+            }
             uint32_t acc[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0u;
@@ -279,46 +294,28 @@ gru_seq_bwd_kernel(const __grid_constant__ BwdArgs a)
 #pragma unroll
                 for (int j = 0; j < 16; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(cor[j]));
             }
-            const int64_t o_t = (int64_t)t * a.R * E;
-            const float *hprev = t > 0 ? a.out + (int64_t)(t - 1) * a.R * E : a.h0;
 #pragma unroll
-            for (int j0 = 0; j0 < HALF; j0 += 8) {
-                float v_do[8], v_r[8], v_z[8], v_n[8], v_hn[8], v_hp[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {          // all global loads first (see the forward kernel)
-                    const int64_t row = row0 + half * HALF + j0 + jj;
-                    v_do[jj] = v_r[jj] = v_z[jj] = v_n[jj] = v_hn[jj] = v_hp[jj] = 0.f;
-                    if (row < a.R) {
-                        const int64_t idx = o_t + row * E + f;
-                        v_do[jj] = __ldg(a.dout + idx);
-                        v_r[jj] = __ldg(a.saves + idx); v_z[jj] = __ldg(a.saves + TRE + idx);
-                        v_n[jj] = __ldg(a.saves + 2 * TRE + idx); v_hn[jj] = __ldg(a.saves + 3 * TRE + idx);
-                        v_hp[jj] = __ldg(hprev + row * E + f);
-                    }
+            for (int j = 0; j < HALF; ++j) {
+                const int n = half * HALF + j;
+                const int64_t row = row0 + n;
+                float dpr = 0.f, dpz = 0.f, dpn = 0.f, dpnr = 0.f;
+                if (row < a.R) {
+                    const float dh = v_do[j] + (dhz[j] + __uint_as_float(acc[j]));
+                    const float r = v_r[j], z = v_z[j], nn = v_n[j], hn = v_hn[j], hp = v_hp[j];
+                    const float dn = dh * (1.f - z);
+                    const float dz = dh * (hp - nn);
+                    dpn = dn * (1.f - nn * nn);
+                    dpz = dz * z * (1.f - z);
+                    dpr = dpn * hn * r * (1.f - r);
+                    dpnr = dpn * r;
+                    dhz[j] = dh * z;
+                    float *gi = a.dgi + ((int64_t)t * a.R + row) * 3 * E + f, *gh = a.dgh + ((int64_t)t * a.R + row) * 3 * E + f;
+                    gi[0] = dpr; gi[E] = dpz; gi[2 * E] = dpn;
+                    gh[0] = dpr; gh[E] = dpz; gh[2 * E] = dpnr;
                 }
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int j = j0 + jj, n = half * HALF + j;
-                    const int64_t row = row0 + n;
-                    float dpr = 0.f, dpz = 0.f, dpn = 0.f, dpnr = 0.f;
-                    if (row < a.R) {
-                        const float dh = v_do[jj] + (dhz[j] + __uint_as_float(acc[j]));
-                        const float r = v_r[jj], z = v_z[jj], nn = v_n[jj], hn = v_hn[jj], hp = v_hp[jj];
-                        const float dn = dh * (1.f - z);
-                        const float dz = dh * (hp - nn);
-                        dpn = dn * (1.f - nn * nn);
-                        dpz = dz * z * (1.f - z);
-                        dpr = dpn * hn * r * (1.f - r);
-                        dpnr = dpn * r;
-                        dhz[j] = dh * z;
-                        float *gi = a.dgi + ((int64_t)t * a.R + row) * 3 * E + f, *gh = a.dgh + ((int64_t)t * a.R + row) * 3 * E + f;
-                        gi[0] = dpr; gi[E] = dpz; gi[2 * E] = dpn;
-                        gh[0] = dpr; gh[E] = dpz; gh[2 * E] = dpnr;
-                    }
-                    TL::store(X, n, f, dpr);
-                    TL::store(X + TL::BYTES, n, f, dpz);
-                    TL::store(X + 2 * TL::BYTES, n, f, dpnr);
-                }
+                TL::store(X, n, f, dpr);
+                TL::store(X + TL::BYTES, n, f, dpz);
+                TL::store(X + 2 * TL::BYTES, n, f, dpnr);
             }
             fence_async_smem();
             fence_before();
@@ -361,7 +358,7 @@ pack_kernel(const float *__restrict__ W, int64_t stride_m, int64_t stride_k, uns
     *reinterpret_cast<float *>(out + off + WPLANE) = lo;
 }
 
-constexpr int FWD_NR = 64, BWD_NR = 32, FWD_STAGES = 5, BWD_STAGES = 4;
+constexpr int FWD_NR = 32, BWD_NR = 32, FWD_STAGES = 6, BWD_STAGES = 4;
 
 }  // namespace gs
 }  // namespace marl
