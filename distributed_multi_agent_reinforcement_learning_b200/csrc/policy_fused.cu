@@ -231,15 +231,24 @@ __device__ __forceinline__ float dot4w(const float (&w)[4], float a0, float a1, 
 }
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// workers: hand X to the issuer, then wait until the group's MMAs have completed
-__device__ __forceinline__ void hand_over(Ctx &c)
+// workers: hand X to the issuer (signal_ready), then wait until the group's MMAs have completed (wait_done).  Work that does not
+// touch X or TMEM — global loads of the NEXT phase's operands — goes between the two, so that its latency hides behind the MMAs.
+__device__ __forceinline__ void signal_ready(Ctx &c)
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     mbar_arrive(c.bar_a_ready);
+}
+__device__ __forceinline__ void wait_done(Ctx &c)
+{
     mbar_wait(c.bar_mma_done, (uint32_t)(c.group & 1));
     tc_fence_after();
     ++c.group;
+}
+__device__ __forceinline__ void hand_over(Ctx &c)
+{
+    signal_ready(c);
+    wait_done(c);
 }
 
 // per-lane slices (channels 4*lane .. 4*lane+3) of one MSG layer, vector loads
@@ -553,52 +562,67 @@ __device__ void phase_fcra_generic(const Ctx &c, int k)
     }
 }
 
+// env-grouped path, split in two: the history rows of the warp's envs are fetched (16 independent 512-byte warp loads, issued
+// while the previous MMA group runs) and then averaged per row from registers
 template <int NA>
-__device__ void phase_fcra_fast(const Ctx &c, int k)
+__device__ __forceinline__ void fcra_prefetch(const Ctx &c, int k, float4 (&h)[16], uint32_t (&words)[4])
 {
     const StepArgs *a = c.a;
     const NetArgs *na = c.na;
     const float *hist = na->hist[k];
-#pragma unroll 1
+#pragma unroll
     for (int g = 0; g < 16 / NA; ++g) {
         const int r0 = 16 * c.warp + g * NA;
         int64_t gr0;
         int env, i0;
         const bool ok = row_info(c, r0, gr0, env, i0);
-        const uint32_t my_word = !ok ? 0u : ((!na->all_ones && c.lane < NA) ? a->p_adj[(gr0 + c.lane) * a->NW] : ((1u << NA) - 1u));
-        float4 h[NA];
+        words[g] = !ok ? 0u : ((!na->all_ones && c.lane < NA) ? a->p_adj[(gr0 + c.lane) * a->NW] : ((1u << NA) - 1u));
 #pragma unroll
-        for (int j = 0; j < NA; ++j)       // all of the env's history rows first: NA independent 512-byte warp loads in flight
-            h[j] = (ok && hist) ? __ldg(reinterpret_cast<const float4 *>(hist + (gr0 + j) * E) + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < NA; ++j)
+            h[g * NA + j] = (ok && hist) ? __ldg(reinterpret_cast<const float4 *>(hist + (gr0 + j) * E) + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int NA>
+__device__ __forceinline__ void fcra_finish(const Ctx &c, const float4 (&h)[16], const uint32_t (&words)[4])
+{
+#pragma unroll
+    for (int g = 0; g < 16 / NA; ++g) {
+        const int r0 = 16 * c.warp + g * NA;
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
-            const uint32_t word = __shfl_sync(0xffffffffu, my_word, i);
+            const uint32_t word = __shfl_sync(0xffffffffu, words[g], i);
             const int cnt = __popc(word & ((1u << NA) - 1u));
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < NA; ++j) {
                 const bool on = (word >> j) & 1u;
-                acc.x += on ? h[j].x : 0.f; acc.y += on ? h[j].y : 0.f; acc.z += on ? h[j].z : 0.f; acc.w += on ? h[j].w : 0.f;
+                const float4 hj = h[g * NA + j];
+                acc.x += on ? hj.x : 0.f; acc.y += on ? hj.y : 0.f; acc.z += on ? hj.z : 0.f; acc.w += on ? hj.w : 0.f;
             }
             const float nrm = cnt ? 1.f / fmaxf((float)cnt, 1e-12f) : 0.f;
             x_store4(c.X, r0 + i, c.lane, make_float4(acc.x * nrm, acc.y * nrm, acc.z * nrm, acc.w * nrm));
         }
     }
 }
-
-__device__ void phase_fcra(const Ctx &c, int k)
+__device__ __forceinline__ void phase_fcra_prefetch(const Ctx &c, int k, float4 (&h)[16], uint32_t (&words)[4])
+{
+    if (!fast_env_path(c.a)) return;
+    if (c.a->N == 8) fcra_prefetch<8>(c, k, h, words);
+    else if (c.a->N == 16) fcra_prefetch<16>(c, k, h, words);
+    else fcra_prefetch<4>(c, k, h, words);
+}
+__device__ __forceinline__ void phase_fcra_finish(const Ctx &c, int k, const float4 (&h)[16], const uint32_t (&words)[4])
 {
     if (!fast_env_path(c.a)) phase_fcra_generic(c, k);
-    else if (c.a->N == 8) phase_fcra_fast<8>(c, k);
-    else if (c.a->N == 16) phase_fcra_fast<16>(c, k);
-    else phase_fcra_fast<4>(c, k);
+    else if (c.a->N == 8) fcra_finish<8>(c, h, words);
+    else if (c.a->N == 16) fcra_finish<16>(c, h, words);
+    else fcra_finish<4>(c, h, words);
 }
 
 // ---- previous hidden state of GRU layer l -> X (16 independent 512-byte warp loads in flight) ----------------------------
-__device__ void phase_load_hidden(const Ctx &c, int l)
+__device__ __forceinline__ void hidden_prefetch(const Ctx &c, int l, float4 (&v)[16])
 {
     const float *h = c.na->hidden + (int64_t)l * c.a->R * E;
-    float4 v[16];
 #pragma unroll
     for (int rr = 0; rr < 16; ++rr) {
         int64_t gr;
@@ -606,6 +630,9 @@ __device__ void phase_load_hidden(const Ctx &c, int l)
         const bool ok = row_info(c, 16 * c.warp + rr, gr, env, i);
         v[rr] = ok ? *(reinterpret_cast<const float4 *>(h + gr * E) + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+__device__ __forceinline__ void hidden_store(const Ctx &c, const float4 (&v)[16])
+{
 #pragma unroll
     for (int rr = 0; rr < 16; ++rr) x_store4(c.X, 16 * c.warp + rr, c.lane, v[rr]);
 }
@@ -679,11 +706,14 @@ __device__ void epi_cell(const Ctx &c, int l, bool want_value)
         PF_TMEM_LD16(az, taddr + (uint32_t)(128 + c0));
         PF_TMEM_LD16(an, taddr + (uint32_t)(256 + c0));
         PF_TMEM_LD16(ahn, taddr + (uint32_t)(384 + c0));
+        float4 hp_all[4];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) hp_all[j >> 2] = x_load4(c.X, row, (c0 + j) >> 2);   // before any store to X (no false dependence)
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
             const int col = c0 + j;
-            const float4 hp4 = x_load4(c.X, row, col >> 2);
+            const float4 hp4 = hp_all[j >> 2];
             const float4 bir = __ldg(reinterpret_cast<const float4 *>(bi + col)), bhr = __ldg(reinterpret_cast<const float4 *>(bh + col));
             const float4 biz = __ldg(reinterpret_cast<const float4 *>(bi + E + col)), bhz = __ldg(reinterpret_cast<const float4 *>(bh + E + col));
             const float4 bin = __ldg(reinterpret_cast<const float4 *>(bi + 2 * E + col)), bhn = __ldg(reinterpret_cast<const float4 *>(bh + 2 * E + col));
@@ -831,10 +861,14 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
         }
         epi_store(c, 128, na->b_sem, false, na->sem_w, na->sem_ld, nullptr);    // h0 (no activation)
         PF_TICK(4);
+        float4 pre[16];
         for (int k = 0; k < a.depth; ++k) {
-            hand_over(c);                                              // FCRA_k, h part -> acc @128
+            uint32_t words[4] = {0u, 0u, 0u, 0u};
+            signal_ready(c);                                           // FCRA_k, h part -> acc @128
+            phase_fcra_prefetch(c, k, pre, words);                     //   ... while it runs: the history rows of the tile
+            wait_done(c);
             PF_TICK(11);
-            phase_fcra(c, k);
+            phase_fcra_finish(c, k, pre, words);
             PF_TICK(5);
             hand_over(c);                                              // AGG_fcra_k -> acc @0
             PF_TICK(11);
@@ -846,9 +880,11 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
             PF_TICK(7);
         }
         for (int l = 0; l < 2; ++l) {
-            hand_over(c);                                              // W_ih: r @0, z @128, n @256
+            signal_ready(c);                                           // W_ih: r @0, z @128, n @256
+            hidden_prefetch(c, l, pre);                                //   ... while it runs: h_prev of this layer
+            wait_done(c);
             PF_TICK(11);
-            phase_load_hidden(c, l);
+            hidden_store(c, pre);
             PF_TICK(8);
             hand_over(c);                                              // W_hh: r += , z +=, hn @384
             PF_TICK(11);
