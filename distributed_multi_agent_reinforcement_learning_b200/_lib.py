@@ -97,6 +97,8 @@ _PROTOTYPES = {
     "marl_rowgemm_pack_bytes": (_I64, [_I32, _I32]),
     "marl_rowgemm_pack": (C.c_int, [_VP, _I64, _I64, _I32, _I32, _VP, _VP]),
     "marl_rowgemm_tf32x3": (C.c_int, [_I64, _I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _VP, _VP, _I64, _VP, _I64, _I32, _VP]),
+    "marl_map_generate": (C.c_int, [_PP, _I32, _I32, C.c_double, C.c_double, C.c_double, _U64, _VP, _VP, _VP]),
+    "marl_env_reset_place": (C.c_int, [_PP, _I32, _I32, _VP, _VP, _U64, C.c_double, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP]),
     "marl_clip_workspace_bytes": (_I64, [_I64]),
     "marl_clip_grad_norm": (C.c_int, [_I64, _VP, _F32, _VP, _VP, _VP]),
     "marl_adam_step": (C.c_int, [_I64, _VP, _VP, _VP, _VP, _F32, _F32, _F32, _F32, _I64, _VP]),

@@ -154,6 +154,32 @@ class BatchedPursuitEnv:
         self.set_state(ps, es, tg, mid, time_step=0)
         self.start_episode()
 
+    def reset_device(self, seed=0, tape_len=16):
+        """Fresh episode for every env, generated ON THE GPU (csrc/reset_kernels.cu): maps, sensor tables, targets, pursuers,
+        evaders and the candidate-target tape.  Same placement rules as `reset` / the reference, per-env counter RNG streams."""
+        import ctypes
+        p, mc = self.params, self.cfg.map
+        _lib.check(self.lib.marl_map_generate(self._pp(), self.M, int(mc.num_obstacle_block), ctypes.c_double(float(mc.center[0])),
+                                              ctypes.c_double(float(mc.center[1])), ctypes.c_double(float(mc.variance)),
+                                              ctypes.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), _lib.ptr(self.grid_bits),
+                                              _lib.ptr(self.inflated_bits), _lib.stream_ptr()), "marl_map_generate")
+        self.build_sensor_tables()
+        if getattr(self, "_reset_scratch", None) is None:
+            self._reset_scratch = torch.empty(self.B, p.W, p.HW, dtype=torch.int32, device=self.device)
+            self.reset_fail = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.marl_env_reset_place(self._pp(), self.B, self.M, _lib.ptr(self.inflated_bits), _lib.ptr(self.map_id),
+                                                 ctypes.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), ctypes.c_double(4.0), 2, 200000,
+                                                 _lib.ptr(self.p_state), _lib.ptr(self.e_state), _lib.ptr(self.target),
+                                                 _lib.ptr(self._reset_scratch), _lib.ptr(self.reset_fail), _lib.stream_ptr()),
+                   "marl_env_reset_place")
+        self.launches += 2
+        g = torch.Generator(device=self.device).manual_seed(int(seed) & 0x7FFFFFFFFFFFFFFF)
+        tape = torch.stack([torch.randint(0, p.W, (self.B, tape_len), generator=g, device=self.device),
+                            torch.randint(0, p.H, (self.B, tape_len), generator=g, device=self.device)], dim=-1).to(torch.int32)
+        self.target_tape, self._tape_len = tape.contiguous(), tape_len
+        self.tape_pos.zero_()
+        self.start_episode()
+
     def start_episode(self):
         self.time_step.zero_()
         self.collision.zero_()

@@ -130,6 +130,22 @@ int marl_evader_replan(const marl_env_params *p, int32_t B, int32_t M, const dou
                        int32_t path_cap, const int32_t *d_time_step, const uint32_t *d_grid_bits,
                        const int32_t *d_map_id, int32_t *d_status, void *stream);
 
+/* ---- episode initialisation on the device -----------------------------------------------------------------------------------
+ * Replaces Pursuit_Env.reset's generators for large batches (pursuit_env.py:60-73 -> base_env.py:37-162, Occupied_Grid_Map.py:46-62).
+ * Same placement RULES as the reference (blocks of 6x6 cells around N(center, variance); target on a free cell of the 2-inflated
+ * map; every pursuer on a free cell, >= min_dist from the earlier ones and within comm range of one or two of them, its
+ * `extend`-inflated footprint then blocked; evader on a free point within sen_range of a pursuer cell), but every map / env draws
+ * from its own counter-based stream keyed by (seed, index): rule- and distribution-equivalent, not stream-equivalent — the
+ * single-env facade keeps the reference's global-RNG order on the host (maps.py).
+ * marl_map_generate: d_grid_bits, d_inflated_bits u32 [M,W,HW] out.
+ * marl_env_reset_place: d_p_state f64 [B,N,4], d_e_state f64 [B,4], d_target i32 [B,2] out (velocities zero); d_scratch u32
+ * [B,W,HW]; d_fail i32 [B] (may be NULL) is 1 where more than max_draws proposals were rejected (over-crowded map). */
+int marl_map_generate(const marl_env_params *p, int32_t M, int32_t num_blocks, double center_x, double center_y, double variance,
+                      uint64_t seed, uint32_t *d_grid_bits, uint32_t *d_inflated_bits, void *stream);
+int marl_env_reset_place(const marl_env_params *p, int32_t B, int32_t M, const uint32_t *d_inflated_bits, const int32_t *d_map_id,
+                         uint64_t seed, double min_dist, int32_t extend, int32_t max_draws, double *d_p_state, double *d_e_state,
+                         int32_t *d_target, uint32_t *d_scratch, int32_t *d_fail, void *stream);
+
 /* ---- kernel 3a: Welford reward normalisation -----------------------------------------------------
  * Replaces Normalization.__call__ / RunningMeanStd.update (DHGN/normalization.py:4-35) applied per env:
  * d_n i64 [B], d_mean f64 [B,N], d_S f64 [B,N], d_std f64 [B,N] (in/out); d_reward i32 [B,N] in;
