@@ -29,6 +29,8 @@ from .replay_buffer import BigBuffer, ReplayBuffer
 
 
 TWO_STREAM_TRAIN = True     # actor and critic branches of a training minibatch on two CUDA streams
+import os as _os
+CONCURRENT_MINIBATCHES = int(_os.environ.get("MARL_CONCURRENT_MB", "3"))  # minibatches of an epoch in flight at once (their clip-accumulate order is replayed afterwards)
 
 
 def orthogonal_init(layer, gain=1.0):
@@ -387,7 +389,7 @@ class MAPPO:
         self.minibuffer, self.total_step, self.cfg = None, 0, cfg
 
     # ------------------------------------------------------------------------------------------------ training
-    def _forward_losses(self, mb, adv, v_target):
+    def _forward_losses(self, mb, adv, v_target, side=None):
         T, B, N, E = mb.T, mb.B, mb.N, self.embedding_dim
         graph = mb.graph()
         enc = self.actor.shared_net
@@ -397,9 +399,10 @@ class MAPPO:
         # kernels of a minibatch only fill 50-100 of the 148 SMs, so the pair overlaps almost perfectly.
         main = torch.cuda.current_stream()
         if TWO_STREAM_TRAIN and not torch.cuda.is_current_stream_capturing():
-            if getattr(self, "_critic_stream", None) is None:
-                self._critic_stream = torch.cuda.Stream(device=self.device)
-            side = self._critic_stream
+            if side is None:
+                if getattr(self, "_critic_stream", None) is None:
+                    self._critic_stream = torch.cuda.Stream(device=self.device)
+                side = self._critic_stream
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 emb_c = enc.encode(graph, True, mb.history("critic"))
@@ -451,22 +454,49 @@ class MAPPO:
         B = tb.B
         bs = self.batch_size or B
         mbs = self.mini_batch_size or bs
-        obj_c = obj_a = 0.0
-        n_updates = 0
-        with torch.enable_grad(), ops.pack_scope():       # weights are fixed for the whole epoch: pack them once
-            for lo in range(0, bs, mbs):
+        # The weights are fixed for the whole epoch, so the minibatches are independent except for the ORDER in which their
+        # gradients enter the running, clipped accumulation (:708-711).  Their forward/backward passes therefore run concurrently
+        # (CONCURRENT_MINIBATCHES in flight, each with its own actor / critic stream pair, gradients into per-minibatch arenas),
+        # and the accumulate-then-clip sequence is replayed afterwards in minibatch order — same result, ~4x the kernels in flight
+        # for the launch-latency-bound GRU sequence kernels.
+        starts = list(range(0, bs, mbs))
+        n_mb = len(starts)
+        flat = self.ac_optimizer.flat_grad
+        views = self.ac_optimizer._views
+        gbuf = torch.zeros(n_mb, flat.numel(), dtype=torch.float32, device=self.device)
+        losses = torch.zeros(n_mb, 2, dtype=torch.float32, device=self.device)
+        main = torch.cuda.current_stream()
+        P = max(1, min(CONCURRENT_MINIBATCHES, n_mb))
+        if getattr(self, "_mb_streams", None) is None or len(self._mb_streams) < P:
+            self._mb_streams = [(torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)) for _ in range(P)]
+        with torch.enable_grad(), ops.pack_scope():       # weights are fixed for the whole epoch: pack them once (per stream)
+            for m, lo in enumerate(starts):
                 hi = min(lo + mbs, bs)
-                mb = tb.minibatch(lo, hi)
-                la, lc, logp, ent, val = self._forward_losses(mb, adv[:, lo:hi].contiguous(), v_target[:, lo:hi].contiguous())
-                (la + lc).backward()
+                st, side = self._mb_streams[m % P]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    mb = tb.minibatch(lo, hi)
+                    la, lc, logp, ent, val = self._forward_losses(mb, adv[:, lo:hi].contiguous(), v_target[:, lo:hi].contiguous(), side=side)
+                    grads = torch.autograd.grad(la + lc, self.ac_parameters, allow_unused=True)
+                    for g, (off, k) in zip(grads, views):
+                        if g is not None:
+                            gbuf[m, off:off + k].copy_(g.reshape(-1))
+                    losses[m, 0], losses[m, 1] = la.detach(), lc.detach()
+                    if trace is not None:
+                        trace.setdefault("mb", []).append(dict(logp=logp.detach(), ent=ent.detach(), val=val.detach()))
+                    del grads, la, lc, logp, ent, val, mb
+            for st, _ in self._mb_streams[:P]:
+                main.wait_stream(st)
+            for m in range(n_mb):                           # gradients accumulate; clip_grad_norm_ acts on the running sum
+                flat.add_(gbuf[m])
                 if self.use_grad_clip:
-                    ops.clip_grad_norm_(self.ac_optimizer.flat_grad, 5.0)
-                if trace is not None:
-                    trace.setdefault("mb", []).append(dict(logp=logp.detach(), ent=ent.detach(), val=val.detach(),
-                                                           actor_loss=float(la), critic_loss=float(lc)))
-                obj_c += float(lc)
-                obj_a += float(la)
-                n_updates += 1
+                    ops.clip_grad_norm_(flat, 5.0)
+        self.ac_optimizer._sync_grads()
+        lh = losses.cpu()
+        if trace is not None:
+            for m, rec in enumerate(trace["mb"]):
+                rec["actor_loss"], rec["critic_loss"] = float(lh[m, 0]), float(lh[m, 1])
+        obj_a, obj_c, n_updates = float(lh[:, 0].sum()), float(lh[:, 1].sum()), n_mb
         if self.use_lr_decay:
             self.lr_decay(total_steps)
         if return_numpy:
