@@ -68,6 +68,7 @@ __device__ __forceinline__ void step_group(const EnvDev &c, const Group<G, APL> 
     bool valid[APL], oob[APL], obst[APL];
     int inner[APL];
     bool lane_oob = false;
+    const DivBy by_tau = make_divby(c.d_tau), by_six = make_divby(6.0);
 #pragma unroll
     for (int a = 0; a < APL; ++a) {
         const int i = g.agent(a);
@@ -77,8 +78,8 @@ __device__ __forceinline__ void step_group(const EnvDev &c, const Group<G, APL> 
         inner[a] = 0;
         if (valid[a]) {
             const double ux = s_table[2 * act[a]], uy = s_table[2 * act[a] + 1];
-            nx[a].vx = rk4_axis(st[a].vx, ux, c.d_tau, c.d_step);
-            nx[a].vy = rk4_axis(st[a].vy, uy, c.d_tau, c.d_step);
+            nx[a].vx = rk4_axis(st[a].vx, ux, by_tau, by_six, c.d_step);
+            nx[a].vy = rk4_axis(st[a].vy, uy, by_tau, by_six, c.d_step);
             nx[a].x = dadd(st[a].x, dmul(nx[a].vx, c.d_step));
             nx[a].y = dadd(st[a].y, dmul(nx[a].vy, c.d_step));
             obst[a] = obstacle_collision(c, grid, nx[a].x, nx[a].y);
@@ -191,9 +192,22 @@ __device__ __forceinline__ void observe_group(const EnvDev &c, const Group<G, AP
         if (env_ok && i < N) {
             // adj[i,j]=1 for i<=j within comm range; adj[j,1]=1 for every j because (j,j) always qualifies
             padj[a][0] = 2u;
-            for (int k = i; k < N; ++k) {
-                const double2 pk = s_pos[k];
-                if (sqnorm2(dsub(st[a].x, pk.x), dsub(st[a].y, pk.y)) <= c.thr2_comm) padj[a][k >> 5] |= 1u << (k & 31);
+            if constexpr (APL == 1) {
+                // N <= G <= 32: one word; every lane walks all G slots (uniform trip count, unrolled, no divergence) and masks
+                // k < i / k >= N afterwards (slots >= N hold stale positions: masked, never stored)
+                uint32_t near = 0u;
+#pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    const double2 pk = s_pos[k];
+                    near |= (sqnorm2(dsub(st[a].x, pk.x), dsub(st[a].y, pk.y)) <= c.thr2_comm ? 1u : 0u) << k;
+                }
+                const uint32_t keep = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) & ~((1u << i) - 1u);
+                padj[a][0] |= near & keep;
+            } else {
+                for (int k = i; k < N; ++k) {
+                    const double2 pk = s_pos[k];
+                    if (sqnorm2(dsub(st[a].x, pk.x), dsub(st[a].y, pk.y)) <= c.thr2_comm) padj[a][k >> 5] |= 1u << (k & 31);
+                }
             }
             eadj[a] = line_of_sight(c, grid, pyround(st[a].x), pyround(st[a].y), exi, eyi);
             const int cx = __double2int_rz(st[a].x), cy = __double2int_rz(st[a].y);   // int(): truncation

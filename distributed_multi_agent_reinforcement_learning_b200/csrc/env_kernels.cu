@@ -19,11 +19,13 @@ __device__ __forceinline__ float welford_one(int x, long long n, double &mean, d
         sd = xd;   // `self.std = x` on the first sample
     } else {
         const double old = mean;
-        mean = dadd(old, ddiv(dsub(xd, old), (double)n));
+        const DivBy by_n = make_divby((double)n);
+        mean = dadd(old, ddiv(dsub(xd, old), by_n));
         S = dadd(S, dmul(dsub(xd, old), dsub(xd, mean)));
-        sd = sqrt(ddiv(S, (double)n));
+        sd = sqrt(ddiv(S, by_n));
     }
-    return (float)ddiv(dsub(xd, mean), dadd(sd, 1e-8));
+    const double num = dsub(xd, mean);
+    return num == 0.0 ? 0.0f : (float)ddiv(num, dadd(sd, 1e-8));     // +0 / positive = +0 without the library's slow path
 }
 
 // ---- kernel 1 --------------------------------------------------------------------------------------------
@@ -242,8 +244,11 @@ struct RolloutArgs {
     int32_t *ev_status;          // [B] OR-ed
 };
 
+#ifndef MARL_ROLLOUT_MIN_BLOCKS
+#define MARL_ROLLOUT_MIN_BLOCKS 5
+#endif
 template <int G, int APL, bool CLOSED>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (APL == 1 ? MARL_ROLLOUT_MIN_BLOCKS : 1))
 rollout_kernel(EnvDev c, RolloutArgs r)
 {
     using Gp = Group<G, APL>;

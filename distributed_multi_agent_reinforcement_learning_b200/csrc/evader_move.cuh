@@ -34,7 +34,8 @@ __device__ __forceinline__ void evader_move(const EnvDev &c, const uint32_t *gri
         phi = dmul(sg, acos(ddiv(dsub(wx, s.x), dadd(radius, 1e-3))));
     }
     const double ux = dmul(cos(phi), c.e_vmax), uy = dmul(sin(phi), c.e_vmax);
-    const double nvx = rk4_axis(s.vx, ux, c.e_tau, c.e_step), nvy = rk4_axis(s.vy, uy, c.e_tau, c.e_step);
+    const DivBy by_tau = make_divby(c.e_tau), by_six = make_divby(6.0);
+    const double nvx = rk4_axis(s.vx, ux, by_tau, by_six, c.e_step), nvy = rk4_axis(s.vy, uy, by_tau, by_six, c.e_step);
     const double nx = dadd(s.x, dmul(nvx, c.e_step)), ny = dadd(s.y, dmul(nvy, c.e_step));
     const int xi = pyround(nx), yi = pyround(ny);
     if (xi >= 0 && xi < c.W && yi >= 0 && yi < c.H && !grid_bit(grid, c.HW, xi, yi)) {   // pursuit_env.py:96-97

@@ -151,19 +151,23 @@ def _wgrad_ok(dy, x):
             and dy.shape[1] % 128 == 0 and x.shape[1] % 128 == 0 and dy.stride(1) == 1 and x.stride(1) == 1)
 
 
-def wgrad(dy, x, out=None, col0=0):
-    """dW = dy^T @ x on the tensor cores (3xTF32, deterministic split-K); writes into out[:, col0 : col0 + x.shape[1]] if given."""
+def wgrad(dy, x, out=None, col0=0, dbias=None):
+    """dW = dy^T @ x on the tensor cores (3xTF32, deterministic split-K); writes into out[:, col0 : col0 + x.shape[1]] if given.
+    dbias (a [N] tensor) additionally receives dy.sum(0), computed by the same kernel from the same loads."""
     R, N = dy.shape
     K = x.shape[1]
     if out is None:
         out = torch.empty(N, K, dtype=torch.float32, device=dy.device)
     if not _wgrad_ok(dy, x):
         out[:, col0:col0 + K] = dy.t() @ x
+        if dbias is not None:
+            dbias.copy_(dy.sum(0))
         return out
     ws = torch.empty(int(_L().marl_wgrad_workspace_bytes(R, N, K)), dtype=torch.uint8, device=dy.device)
     dst = out[:, col0:]
-    _lib.check(_L().marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dst.data_ptr(), out.stride(0), 0,
-                                      ws.data_ptr(), _lib.stream_ptr()), "marl_wgrad_tf32x3")
+    _lib.check(_L().marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dst.data_ptr(), out.stride(0),
+                                      dbias.data_ptr() if dbias is not None else None, 0, ws.data_ptr(), _lib.stream_ptr()),
+               "marl_wgrad_tf32x3")
     return out
 
 
@@ -190,14 +194,17 @@ class _LinearTC(torch.autograd.Function):
             dx = _gemm_tc(dy, None, W[:, :K1], None, None, False, transposed=True) if _tc_t_ok(dy, W[:, :K1]) else dy @ W[:, :K1]
         if has_x2 and need[1]:
             dx2 = _gemm_tc(dy, None, W[:, K1:], None, None, False, transposed=True) if _tc_t_ok(dy, W[:, K1:]) else dy @ W[:, K1:]
-        if need[2]:   # weight gradient: reduction over the (huge) row dimension -> split-K tensor-core kernel
+        want_db = has_bias and need[3]
+        if want_db:
+            db = torch.empty(W.shape[0], dtype=torch.float32, device=dy.device)
+        if need[2]:   # weight gradient: reduction over the (huge) row dimension -> split-K tensor-core kernel (+ fused bias gradient)
             if has_x2:
                 dW = torch.empty(W.shape[0], W.shape[1], dtype=torch.float32, device=dy.device)
-                wgrad(dy, x, dW, 0)
+                wgrad(dy, x, dW, 0, dbias=db if want_db else None)
                 wgrad(dy, x2, dW, K1)
             else:
-                dW = wgrad(dy, x)
-        if has_bias and need[3]:
+                dW = wgrad(dy, x, dbias=db if want_db else None)
+        elif want_db:
             db = dy.sum(0)
         if has_add and need[4]:
             dadd = dy
@@ -327,7 +334,9 @@ class _GRULayer(torch.autograd.Function):
             dgi2, dgh2 = dgi.view(T * R, 3 * E), dgh.view(T * R, 3 * E)
             h_prev_all = torch.cat([h0c.unsqueeze(0), out[:-1]], dim=0).view(T * R, E)
             dx = (_gemm_tc(dgi2, None, w_ih, None, None, False, transposed=True) if _tc_t_ok(dgi2, w_ih) else torch.mm(dgi2, w_ih)).view(T, R, E)
-            return dx, dh0, wgrad(dgi2, x.view(T * R, E)), wgrad(dgh2, h_prev_all), dgi2.sum(0), dgh2.sum(0)
+            db_ih = torch.empty(3 * E, dtype=x.dtype, device=x.device)
+            db_hh = torch.empty(3 * E, dtype=x.dtype, device=x.device)
+            return (dx, dh0, wgrad(dgi2, x.view(T * R, E), dbias=db_ih), wgrad(dgh2, h_prev_all, dbias=db_hh), db_ih, db_hh)
         x, h0, w_ih, w_hh, out, saves = ctx.saved_tensors
         T, R, E = x.shape
         d_out = d_out.contiguous()

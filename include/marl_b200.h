@@ -397,12 +397,13 @@ int marl_gru_seq_bwd(int32_t T, int64_t R, int32_t E, const float *d_dout, const
 
 /* Weight gradient of a dense layer on the tcgen05 tensor cores (3xTF32, fp32-level accuracy, deterministic split-K):
  * dW[n][k] (+)= sum_{r<R} dY[r][n] X[r][k], dY f32 [R, N_out] (row stride lddy), X f32 [R, K_in] (row stride ldx), dW row stride
- * lddw (so the two halves of a concatenated input can be written into column ranges of one gradient).  Replaces the autograd
+ * lddw (so the two halves of a concatenated input can be written into column ranges of one gradient); d_dbias (may be NULL)
+ * f32 [N_out] receives sum_r dY[r][:] (the bias gradient) from the same loads.  Replaces the autograd
  * weight-gradient GEMMs behind `ac_loss.backward()` (DHGN/mappo_parallel.py:708).  N_out, K_in multiples of 128.
  * d_workspace: marl_wgrad_workspace_bytes(R, N_out, K_in) bytes. */
 int64_t marl_wgrad_workspace_bytes(int64_t R, int32_t N_out, int32_t K_in);
 int marl_wgrad_tf32x3(int64_t R, int32_t N_out, int32_t K_in, const float *d_dY, int64_t lddy, const float *d_X, int64_t ldx,
-                      float *d_dW, int64_t lddw, int32_t accumulate, void *d_workspace, void *stream);
+                      float *d_dW, int64_t lddw, float *d_dbias, int32_t accumulate, void *d_workspace, void *stream);
 
 /* Persistent row-tile GEMM for training (forward and input-gradient GEMMs of every E-wide layer), tcgen05 3xTF32:
  * C[M,N] = act([A1 | A2] B^T + bias + D), B[N, K1+K2] given pre-packed by marl_rowgemm_pack from any strided view

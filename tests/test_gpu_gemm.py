@@ -103,10 +103,13 @@ def test_wgrad_tf32x3_matches_fp64(R, N, K, ldx_extra):
     outs = []
     for _ in range(2):
         dW = torch.full((N, K + 8), 7.0, device="cuda")
-        _lib.check(L.marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dW.data_ptr(), dW.stride(0), 0,
-                                       ws.data_ptr(), _lib.stream_ptr()), "marl_wgrad_tf32x3")
+        db = torch.full((N,), 3.0, device="cuda")
+        _lib.check(L.marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dW.data_ptr(), dW.stride(0),
+                                       db.data_ptr(), 0, ws.data_ptr(), _lib.stream_ptr()), "marl_wgrad_tf32x3")
         torch.cuda.synchronize()
         outs.append(dW.clone())
+        bref = dy.double().sum(0)
+        assert (db.double() - bref).abs().max().item() <= 2e-6 * max(1.0, bref.abs().max().item()) * (R ** 0.5)
     assert torch.equal(outs[0], outs[1])
     assert (outs[0][:, K:] == 7.0).all()                       # nothing written outside the tile columns
     err = (outs[0][:, :K].double() - ref).abs().max().item()
@@ -114,7 +117,7 @@ def test_wgrad_tf32x3_matches_fp64(R, N, K, ldx_extra):
     fp32 = ((dy.t() @ x).double() - ref).abs().max().item()    # what the library sgemm achieves
     assert err <= max(5e-6 * scale, 4.0 * fp32), (err, fp32, scale)      # fp32-level: a few ulp of the accumulated magnitude
     # accumulate mode
-    _lib.check(L.marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dW.data_ptr(), dW.stride(0), 1,
+    _lib.check(L.marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dW.data_ptr(), dW.stride(0), None, 1,
                                    ws.data_ptr(), _lib.stream_ptr()), "marl_wgrad_tf32x3")
     torch.testing.assert_close(dW[:, :K], 2 * outs[0][:, :K], rtol=1e-6, atol=1e-6 * scale)
 
