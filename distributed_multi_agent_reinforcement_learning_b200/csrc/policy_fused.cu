@@ -5,8 +5,11 @@
 // the history embeddings in, the new embedding, hidden states and action / log-prob / value out.
 //
 // Tensor cores: every 128-wide dense layer is a chain of "units" (one unit = [128 rows x K=128] x [K=128 x n_out]) issued as
-// tcgen05.mma.kind::tf32 with fp32 accumulation in TMEM.  fp32-level accuracy comes from the 3xTF32 split
-// (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, see gemm_tf32x3.cu); the weights are pre-split and pre-swizzled once per rollout
+// tcgen05.mma.kind::f16 with fp32 accumulation in TMEM.  fp32-level accuracy comes from a two-term fp16 split of BOTH operands,
+// a = hi + lo with hi = fp16(a), lo = fp16(a - hi) (22 significant bits; |a - (hi + lo)| <= 2^-23 |a|, or 2^-25 absolute once lo is
+// an fp16 subnormal, i.e. |a| < 1/8 - tensor cores take subnormal inputs exactly), and three products per K step
+// (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, the 2^-22 lo*lo term is dropped - the same error budget as 3xTF32, see gemm_tf32x3.cu) at
+// twice the TF32 rate and half the operand bytes.  The weights are pre-split and pre-swizzled once per rollout
 // (marl_policy_pack) into the exact shared-memory image of each k-block, so that the producer is a single elected thread
 // issuing cp.async.bulk copies (32 KB per stage) that complete on an mbarrier.
 //
@@ -14,23 +17,24 @@
 //   warps 0-7  workers: SIMT phases (messages, FCRA neighbour mean, hidden-state load) that write the activation tile X
 //              straight into the canonical K-major SWIZZLE_128B operand layout (hi and lo planes), and the epilogues
 //              (tcgen05.ld -> bias / ReLU / GRU cell / heads -> X again, plus the few global stores);
-//   warp 8     weight loader (elected lane): streams the packed units through a 3-stage ring;
+//   warp 8     weight loader (elected lane): streams the packed units through a 4-stage ring;
 //   warp 9     MMA issuer (elected lane) + TMEM allocation (all 512 columns: the GRU needs four 128-column accumulators).
 // Workers and the issuer follow the same static unit program and hand the tile back and forth with two mbarriers
 // (a_ready: 256 arrivals, mma_done: tcgen05.commit).
-// Shared memory: X 128 KB (4 k-blocks x (hi 16 KB + lo 16 KB)) + 3 x 32 KB weight stages.
+// Shared memory: X 64 KB (2 k-blocks of K = 64 x (hi 16 KB + lo 16 KB)) + 4 x 32 KB weight stages.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace marl {
 namespace pf {
 
-constexpr int ROWS = 128, E = 128, NSTAGE = 3, MAXD = 3, MAX_UNITS = 40;
+constexpr int ROWS = 128, E = 128, NSTAGE = 4, MAXD = 3, MAX_UNITS = 40, NKB = 2 /* k-blocks of 64 halves per K = 128 */;
 constexpr int BAR_A_READY = 2 * NSTAGE, BAR_MMA_DONE = 2 * NSTAGE + 1;
-constexpr int TILE = ROWS * 128;          // 16 KB: 128 rows x 128 B (one k-block of 32 floats)
+constexpr int TILE = ROWS * 128;          // 16 KB: 128 rows x 128 B (one k-block of 64 halves)
 constexpr int XKB = 2 * TILE;             // one k-block of X: hi plane + lo plane
-constexpr int X_BYTES = 4 * XKB;          // K = 128
+constexpr int X_BYTES = NKB * XKB;        // K = 128
 constexpr int WSTAGE = 2 * TILE;          // one k-block of a 128-row weight unit: hi + lo
-constexpr int SMEM_BYTES = X_BYTES + NSTAGE * WSTAGE + 3072 /*barriers, fp32 state of the tile*/;   // 232 448 B = 227 KB
+constexpr int SMEM_BYTES = X_BYTES + NSTAGE * WSTAGE + 3072 /*barriers, fp32 state of the tile*/;   // 195 KB
 constexpr int WORKERS = 256, THREADS = 320;
 
 struct Unit {
@@ -121,14 +125,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;
     return d;
 }
-__device__ __forceinline__ uint32_t idesc_tf32(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+// kind::f16 instruction descriptor: D = f32 (bit 4), A = B = f16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -160,32 +165,59 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
         : "r"(addr))
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// hi = a rounded to TF32 precision with the discarded bits cleared; lo = a - hi EXACTLY (all 23 mantissa bits kept, the
-// tensor core reads its top 10): hi + lo == a, so an activation can be read back from X at full fp32 precision.
-__device__ __forceinline__ void split_tf32(float a, float &hi, float &lo)
+// two-term fp16 split of a pair: hi = fp16(a) (saturating: the network's activations are far below 65504), lo = fp16(a - hi);
+// hi + lo reproduces a to one fp32 ulp (2^-25 absolute below 1/8), so activations are read back from X at fp32 level.
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t &hi, uint32_t &lo)
 {
-    const uint32_t u = __float_as_uint(a);
-    hi = __uint_as_float((u + 0x1000u) & 0xFFFFE000u);
-    lo = a - hi;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));          // low half = a, high half = b
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hf.y), "f"(a - hf.x));
 }
-__device__ __forceinline__ int x_off(int row, int c4) { return (c4 >> 3) * XKB + row * 128 + (((c4 & 7) ^ (row & 7)) << 4); }
-// element group (row, channels 4*c4 .. 4*c4+3) of the activation tile, both planes
+__device__ __forceinline__ float2 join_h2(uint32_t hi, uint32_t lo)
+{
+    const float2 h = __half22float2(*reinterpret_cast<const __half2 *>(&hi)), l = __half22float2(*reinterpret_cast<const __half2 *>(&lo));
+    return make_float2(h.x + l.x, h.y + l.y);
+}
+// K-major SWIZZLE_128B: a row of a k-block is 128 B = 64 halves; 16-byte chunk index XOR (row & 7)
+__device__ __forceinline__ int x_off(int row, int c4) { return (c4 >> 4) * XKB + row * 128 + ((((c4 & 15) >> 1) ^ (row & 7)) << 4) + (c4 & 1) * 8; }
+// element group (row, channels 4*c4 .. 4*c4+3) of the activation tile, both planes (8-byte accesses: conflict-free when the 32
+// lanes of a warp walk c4 of one row, which is how the SIMT phases use it)
 __device__ __forceinline__ void x_store4(unsigned char *X, int row, int c4, float4 v)
 {
-    float4 h, l;
-    split_tf32(v.x, h.x, l.x);
-    split_tf32(v.y, h.y, l.y);
-    split_tf32(v.z, h.z, l.z);
-    split_tf32(v.w, h.w, l.w);
+    uint2 h, l;
+    split_h2(v.x, v.y, h.x, l.x);
+    split_h2(v.z, v.w, h.y, l.y);
     const int off = x_off(row, c4);
-    *reinterpret_cast<float4 *>(X + off) = h;
-    *reinterpret_cast<float4 *>(X + off + TILE) = l;
+    *reinterpret_cast<uint2 *>(X + off) = h;
+    *reinterpret_cast<uint2 *>(X + off + TILE) = l;
 }
 __device__ __forceinline__ float4 x_load4(const unsigned char *X, int row, int c4)
 {
     const int off = x_off(row, c4);
-    const float4 h = *reinterpret_cast<const float4 *>(X + off), l = *reinterpret_cast<const float4 *>(X + off + TILE);
-    return make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+    const uint2 h = *reinterpret_cast<const uint2 *>(X + off), l = *reinterpret_cast<const uint2 *>(X + off + TILE);
+    const float2 a = join_h2(h.x, l.x), b = join_h2(h.y, l.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+// channels 8*c8 .. 8*c8+7 of one row (16-byte accesses: conflict-free when the lanes of a warp are 32 consecutive rows, which is
+// how the epilogues use it)
+__device__ __forceinline__ int x_off8(int row, int c8) { return (c8 >> 3) * XKB + row * 128 + (((c8 & 7) ^ (row & 7)) << 4); }
+__device__ __forceinline__ void x_store8(unsigned char *X, int row, int c8, const float (&v)[8])
+{
+    uint4 h, l;
+    split_h2(v[0], v[1], h.x, l.x);
+    split_h2(v[2], v[3], h.y, l.y);
+    split_h2(v[4], v[5], h.z, l.z);
+    split_h2(v[6], v[7], h.w, l.w);
+    const int off = x_off8(row, c8);
+    *reinterpret_cast<uint4 *>(X + off) = h;
+    *reinterpret_cast<uint4 *>(X + off + TILE) = l;
+}
+__device__ __forceinline__ void x_load8(const unsigned char *X, int row, int c8, float (&v)[8])
+{
+    const int off = x_off8(row, c8);
+    const uint4 h = *reinterpret_cast<const uint4 *>(X + off), l = *reinterpret_cast<const uint4 *>(X + off + TILE);
+    const float2 a = join_h2(h.x, l.x), b = join_h2(h.y, l.y), c = join_h2(h.z, l.z), d = join_h2(h.w, l.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
 
 struct Ctx {
@@ -637,7 +669,7 @@ __device__ __forceinline__ void hidden_store(const Ctx &c, const float4 (&v)[16]
     for (int rr = 0; rr < 16; ++rr) x_store4(c.X, 16 * c.warp + rr, c.lane, v[rr]);
 }
 
-// X (exact fp32 = hi + lo) -> global rows, coalesced: warp w copies rows 16w..16w+15, 512 bytes per row
+// X (hi + lo: fp32 to one ulp) -> global rows, coalesced: warp w copies rows 16w..16w+15, 512 bytes per row
 __device__ void copy_out(const Ctx &c, float *g)
 {
 #pragma unroll 4
@@ -663,21 +695,23 @@ __device__ void epi_store(const Ctx &c, int acc_col, const float *bias, bool rel
         PF_TMEM_LD32(v, taddr + (uint32_t)c0);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 32; j += 8) {
             const int col = c0 + j;
-            const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
-            float4 o = make_float4(__uint_as_float(v[j]) + bb.x, __uint_as_float(v[j + 1]) + bb.y, __uint_as_float(v[j + 2]) + bb.z,
-                                   __uint_as_float(v[j + 3]) + bb.w);
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + col)), b1 = __ldg(reinterpret_cast<const float4 *>(bias + col + 4));
+            float o[8] = {__uint_as_float(v[j]) + b0.x, __uint_as_float(v[j + 1]) + b0.y, __uint_as_float(v[j + 2]) + b0.z, __uint_as_float(v[j + 3]) + b0.w,
+                          __uint_as_float(v[j + 4]) + b1.x, __uint_as_float(v[j + 5]) + b1.y, __uint_as_float(v[j + 6]) + b1.z, __uint_as_float(v[j + 7]) + b1.w};
             if (wp) {
-                float *of = reinterpret_cast<float *>(&o);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 8; ++q) {
                     const float4 wv = __ldg(reinterpret_cast<const float4 *>(wp + (int64_t)(col + q) * wp_ld));
-                    of[q] += fmaf(wv.w, p.w, fmaf(wv.z, p.z, fmaf(wv.y, p.y, fmaf(wv.x, p.x, 0.f))));
+                    o[q] += fmaf(wv.w, p.w, fmaf(wv.z, p.z, fmaf(wv.y, p.y, fmaf(wv.x, p.x, 0.f))));
                 }
             }
-            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            x_store4(c.X, row, col >> 2, o);
+            if (relu) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = fmaxf(o[q], 0.f);
+            }
+            x_store8(c.X, row, col >> 3, o);
         }
     }
     if (gout) {
@@ -690,7 +724,7 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 // ---- epilogue: GRU cell of layer l (torch gate order r, z, n); h' -> X (then coalesced to global); critic layer 1: value ---
-// h_prev is read back from X (it is the A operand of the W_hh group, exact fp32).  The gates use ex2-based exp and the fast
+// h_prev is read back from X (it is the A operand of the W_hh group; hi + lo = fp32 to one ulp).  The gates use ex2-based exp and the fast
 // division (abs error ~1e-7, inside the 1e-5 forward tolerance).
 __device__ void epi_cell(const Ctx &c, int l, bool want_value)
 {
@@ -706,14 +740,15 @@ __device__ void epi_cell(const Ctx &c, int l, bool want_value)
         PF_TMEM_LD16(az, taddr + (uint32_t)(128 + c0));
         PF_TMEM_LD16(an, taddr + (uint32_t)(256 + c0));
         PF_TMEM_LD16(ahn, taddr + (uint32_t)(384 + c0));
-        float4 hp_all[4];
+        float hp_all[2][8];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) hp_all[j >> 2] = x_load4(c.X, row, (c0 + j) >> 2);   // before any store to X (no false dependence)
+        for (int j = 0; j < 16; j += 8) x_load8(c.X, row, (c0 + j) >> 3, hp_all[j >> 3]);   // before any store to X (no false dependence)
         tmem_wait_ld();
+        float hn_all[2][8];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
             const int col = c0 + j;
-            const float4 hp4 = hp_all[j >> 2];
+            const float4 hp4 = make_float4(hp_all[j >> 3][j & 4], hp_all[j >> 3][(j & 4) + 1], hp_all[j >> 3][(j & 4) + 2], hp_all[j >> 3][(j & 4) + 3]);
             const float4 bir = __ldg(reinterpret_cast<const float4 *>(bi + col)), bhr = __ldg(reinterpret_cast<const float4 *>(bh + col));
             const float4 biz = __ldg(reinterpret_cast<const float4 *>(bi + E + col)), bhz = __ldg(reinterpret_cast<const float4 *>(bh + E + col));
             const float4 bin = __ldg(reinterpret_cast<const float4 *>(bi + 2 * E + col)), bhn = __ldg(reinterpret_cast<const float4 *>(bh + 2 * E + col));
@@ -733,8 +768,11 @@ __device__ void epi_cell(const Ctx &c, int l, bool want_value)
                 hn[q] = (1.f - z) * n + z * hp[q];
                 vdot = fmaf(f_w[q], hn[q], vdot);
             }
-            x_store4(c.X, row, col >> 2, make_float4(hn[0], hn[1], hn[2], hn[3]));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hn_all[j >> 3][(j & 4) + q] = hn[q];
         }
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) x_store8(c.X, row, (c0 + j) >> 3, hn_all[j >> 3]);
     }
     if (want_value) c.s_val[hh * ROWS + row] = vdot;
     worker_sync();
@@ -799,7 +837,8 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
     unsigned char *X = smem;
     unsigned char *Wst = smem + X_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + X_BYTES + NSTAGE * WSTAGE);   // full[NSTAGE], empty[NSTAGE], a_ready, mma_done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGE + 2);
+    static_assert(2 * NSTAGE + 3 <= 16, "barrier block");
     float4 *s_p = reinterpret_cast<float4 *>(bars + 16);                                  // 128 x float4 (later: s_val)
     float4 *s_e = s_p + ROWS;                                                               // 32 x float4
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -908,7 +947,7 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
             for (int u = 0; u < na->n_units; ++u) {
                 const Unit un = na->u[u];
                 const uint32_t bytes = 2u * un.n_out * 128u;
-                for (int kb = 0; kb < 4; ++kb, ++it) {
+                for (int kb = 0; kb < NKB; ++kb, ++it) {
                     const int s = it % NSTAGE, round = it / NSTAGE;
                     if (round > 0) mbar_wait(smem_u32(&bars[NSTAGE + s]), (uint32_t)((round - 1) & 1));
                     mbar_expect_tx(smem_u32(&bars[s]), bytes);
@@ -928,22 +967,22 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
                     tc_fence_after();
                     fresh_group = false;
                 }
-                const uint32_t idesc = idesc_tf32(un.n_out);
+                const uint32_t idesc = idesc_f16(un.n_out);
                 const uint32_t acc = tmem_base + un.acc_col;
                 const uint32_t lo_off = (uint32_t)un.n_out * 128u;
-                for (int kb = 0; kb < 4; ++kb, ++it) {
+                for (int kb = 0; kb < NKB; ++kb, ++it) {
                     const int s = it % NSTAGE, round = it / NSTAGE;
                     mbar_wait(smem_u32(&bars[s]), (uint32_t)(round & 1));
                     tc_fence_after();
                     const uint32_t xa = smem_u32(X + kb * XKB), wb = smem_u32(Wst + s * WSTAGE);
-                    // descriptors of the first K=8 slice; the next slices are +32 bytes = +2 in the (addr >> 4) field
+                    // descriptors of the first K=16 slice; the next slices are +32 bytes = +2 in the (addr >> 4) field
                     const uint64_t a_hi0 = make_desc(xa), a_lo0 = make_desc(xa + TILE), b_hi0 = make_desc(wb), b_lo0 = make_desc(wb + lo_off);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint64_t a_hi = a_hi0 + 2 * kk, a_lo = a_lo0 + 2 * kk, b_hi = b_hi0 + 2 * kk, b_lo = b_lo0 + 2 * kk;
-                        umma_tf32(acc, a_hi, b_hi, idesc, (un.accumulate || kb || kk) ? 1u : 0u);
-                        umma_tf32(acc, a_lo, b_hi, idesc, 1u);
-                        umma_tf32(acc, a_hi, b_lo, idesc, 1u);
+                        umma_f16(acc, a_hi, b_hi, idesc, (un.accumulate || kb || kk) ? 1u : 0u);
+                        umma_f16(acc, a_lo, b_hi, idesc, 1u);
+                        umma_f16(acc, a_hi, b_lo, idesc, 1u);
                     }
                     umma_commit(smem_u32(&bars[NSTAGE + s]));
                 }
@@ -960,7 +999,7 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
     if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
-// ---- weight packing: one unit = W[rows, k0 : k0+128] -> 4 k-blocks x (hi plane, lo plane) in the smem image ------------------
+// ---- weight packing: one unit = W[rows, k0 : k0+128] -> 2 k-blocks (K = 64) x (hi plane, lo plane) in the smem image ------------
 __global__ void __launch_bounds__(256)
 pack_unit_kernel(const float *__restrict__ W, int64_t ld, int rows_valid, int n_out, int k0, unsigned char *__restrict__ out)
 {
@@ -968,13 +1007,13 @@ pack_unit_kernel(const float *__restrict__ W, int64_t ld, int rows_valid, int n_
     if (idx >= n_out * 128) return;
     const int n = idx >> 7, k = idx & 127;
     const float v = n < rows_valid ? W[(int64_t)n * ld + k0 + k] : 0.f;
-    float hi, lo;
-    split_tf32(v, hi, lo);
-    const int kb = k >> 5, kk = k & 31;
+    uint32_t hi, lo;
+    split_h2(v, 0.f, hi, lo);
+    const int kb = k >> 6, kk = k & 63;
     const size_t plane = (size_t)n_out * 128;
-    const size_t off = (size_t)kb * 2 * plane + (size_t)n * 128 + ((((kk >> 2) ^ (n & 7))) << 4) + (kk & 3) * 4;
-    *reinterpret_cast<float *>(out + off) = hi;
-    *reinterpret_cast<float *>(out + off + plane) = lo;
+    const size_t off = (size_t)kb * 2 * plane + (size_t)n * 128 + ((((kk >> 3) ^ (n & 7))) << 4) + (kk & 7) * 2;
+    *reinterpret_cast<unsigned short *>(out + off) = (unsigned short)(hi & 0xffffu);
+    *reinterpret_cast<unsigned short *>(out + off + plane) = (unsigned short)(lo & 0xffffu);
 }
 
 struct UnitSrc {
@@ -1008,7 +1047,30 @@ static int build_units(const marl_dhgn_weights *w, int depth, int is_actor, int 
     return n;
 }
 
-static int64_t unit_bytes(int n_out) { return (int64_t)n_out * 1024; }
+// Rows per work item: whole envs, at most 128 rows (one MMA M tile).  One CTA is resident per SM, so the launch runs in
+// ceil(items / SMs) waves; a slightly smaller tile that fills the last wave beats a full tile that leaves most SMs idle in it
+// (32768 rows x 2 networks: 512 items of 128 rows = 3.46 -> 4 waves, 586 items of 112 rows = 3.96 waves).  Cost model of one item:
+// SIMT phases proportional to the rows, MMA phases constant (M = 128 regardless) - measured ~3 : 1 at 128 rows.
+static int choose_rows_per_tile(int64_t R, int N, int nets)
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int full = (ROWS / N) * N;
+    int best = full;
+    double best_cost = 0.0;
+    for (int rpt = full; rpt >= N && rpt * 4 >= full * 3; rpt -= N) {
+        const int64_t items = ((R + rpt - 1) / rpt) * nets;
+        const double waves = (double)((items + sms - 1) / sms);
+        const double cost = waves * (0.75 * rpt / full + 0.25);
+        if (best_cost == 0.0 || cost < best_cost - 1e-12) { best_cost = cost; best = rpt; }
+    }
+    return best;
+}
+
+static int64_t unit_bytes(int n_out) { return (int64_t)n_out * 128 * 2 * NKB; }
 
 static int check_weights(const marl_dhgn_weights *w, int depth, int is_actor)
 {
@@ -1097,8 +1159,9 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
     MARL_REQUIRE((actor_w && actor_io) || (critic_w && critic_io), "marl_policy_rollout_step: no network given");
     pf::StepArgs a{};
     a.B = s->B; a.N = s->N; a.O = s->O; a.NW = (s->N + 31) / 32; a.OW = (s->O + 31) / 32; a.depth = s->depth; a.A = s->action_dim;
-    a.rows_per_tile = (pf::ROWS / s->N) * s->N;
     a.R = (int64_t)s->B * s->N;
+    const int nets = ((actor_w && actor_io) ? 1 : 0) + ((critic_w && critic_io) ? 1 : 0);
+    a.rows_per_tile = pf::choose_rows_per_tile(a.R, s->N, nets);
     a.n_tiles = (int)((a.R + a.rows_per_tile - 1) / a.rows_per_tile);
     a.p_state = s->d_p_state; a.e_state = s->d_e_state; a.oxy = s->d_oxy; a.map_id = s->d_map_id; a.o_count = s->d_o_count;
     a.p_adj = s->d_p_adj_bits; a.e_adj = s->d_e_adj; a.o_adj = s->d_o_adj_bits;

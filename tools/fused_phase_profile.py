@@ -32,8 +32,8 @@ emb_a, emb_c = torch.empty(B, N, E, device=dev), torch.empty(B, N, E, device=dev
 act, logp, val = torch.zeros(B, N, dtype=torch.int32, device=dev), torch.empty(B, N, device=dev), torch.empty(B, N, device=dev)
 hist = [0.1 * torch.randn(B, N, E, device=dev)]
 env.observe()
-n_tiles = (B * N + 127) // 128
-dbg = torch.zeros(2 * n_tiles, 16, dtype=torch.int64, device=dev)
+n_tiles = (B * N + 127) // 128   # upper bound is 4/3 of this (the kernel may pick tiles down to 96 rows)
+dbg = torch.zeros(2 * ((4 * n_tiles + 2) // 3), 16, dtype=torch.int64, device=dev)
 for it in range(3):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -45,6 +45,9 @@ for it in range(3):
 d = dbg.cpu().numpy().astype(np.float64)
 names = ["msg0", "msg1", "msg2", "epi_av(x3)", "epi_sem", "fcra", "epi_aggf", "epi_f", "load_hidden(x2)", "epi_cell(x2)", "head",
          "wait_mma(all)", "total"]
+d = d[d[:, 12] > 0]            # CTAs that ran (critic items first, then the actor's)
+n_tiles = len(d) // 2
+print("items", len(d), "rows per tile ~", -(-B * N // max(n_tiles, 1)))
 for label, rows in (("critic", d[:n_tiles]), ("actor", d[n_tiles:])):
     print(label, "tiles", len(rows))
     for i, n in enumerate(names):
