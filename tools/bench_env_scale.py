@@ -11,9 +11,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from distributed_multi_agent_reinforcement_learning_b200 import _lib, default_config  # noqa: E402
-if os.environ.get("MARL_AB_LIB"):        # A/B runs of kernel variants (tools only)
-    _lib.LIB_PATH = os.path.abspath(os.environ["MARL_AB_LIB"])
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import ab  # noqa: E402,F401
+from distributed_multi_agent_reinforcement_learning_b200 import default_config  # noqa: E402
 from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv, RolloutArena  # noqa: E402
 
 
