@@ -34,7 +34,10 @@ constexpr int TILE = ROWS * 128;          // 16 KB: 128 rows x 128 B (one k-bloc
 constexpr int XKB = 2 * TILE;             // one k-block of X: hi plane + lo plane
 constexpr int X_BYTES = NKB * XKB;        // K = 128
 constexpr int WSTAGE = 2 * TILE;          // one k-block of a 128-row weight unit: hi + lo
-constexpr int SMEM_BYTES = X_BYTES + NSTAGE * WSTAGE + 3072 /*barriers, fp32 state of the tile*/;   // 195 KB
+constexpr int MISC_BYTES = 3072;           // barriers, fp32 state of the tile
+constexpr int OXY_CAP = 256;               // boundary cells of one map staged per worker warp (fast message path: O <= 256)
+constexpr int OXY_BYTES = 8 * OXY_CAP * 8; // 8 worker warps x 256 float2
+constexpr int SMEM_BYTES = X_BYTES + NSTAGE * WSTAGE + MISC_BYTES + OXY_BYTES;   // 211 KB
 constexpr int WORKERS = 256, THREADS = 320;
 
 struct Unit {
@@ -231,6 +234,7 @@ struct Ctx {
     float4 *s_p;         // [128] fp32 pursuer state of the tile's rows (converted once)
     float4 *s_e;         // [32] fp32 evader state of the tile's envs (when the tile has <= 32 envs)
     float *s_val;        // [2][128] scratch for the critic value (aliases s_p, which is dead by then)
+    float2 *s_oxy;       // [8 warps][OXY_CAP] boundary cells of the env a warp is working on (obstacle relation)
 };
 
 __device__ __forceinline__ bool row_info(const Ctx &c, int r, int64_t &gr, int &env, int &i)
@@ -464,18 +468,21 @@ __device__ void phase_msg_fast(const Ctx &c, int rel)
         } else {
             const int m = a->map_id ? a->map_id[env] : env;
             const int2 *oxy = reinterpret_cast<const int2 *>(a->oxy) + (int64_t)m * a->O;
-            float2 my_o[8];
+            // the map's boundary cells -> this warp's shared-memory staging (one broadcast LDS.64 per cell in the loops below;
+            // the loops are unrolled so that several cells are in flight)
+            float2 *so = c.s_oxy + c.warp * OXY_CAP;
+            __syncwarp();                                      // the previous env's readers are done
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                my_o[t] = make_float2(0.f, 0.f);
                 const int k = lane + 32 * t;
-                if (t < a->OW && k < a->O) { const int2 o = __ldg(oxy + k); my_o[t] = make_float2((float)o.x, (float)o.y); }
+                if (t < a->OW && k < a->O) { const int2 o = __ldg(oxy + k); so[k] = make_float2((float)o.x, (float)o.y); }
             }
+            __syncwarp();
             if (na->all_ones) {
                 const int n = a->o_count[m];
                 float sx = 0.f, sy = 0.f;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) if (lane + 32 * t < n) { sx += my_o[t].x; sy += my_o[t].y; }
+                for (int t = 0; t < 8; ++t) if (lane + 32 * t < n) { const float2 o = so[lane + 32 * t]; sx += o.x; sy += o.y; }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
                 const float nrm = n ? 1.f / fmaxf((float)n, 1e-12f) : 0.f;
@@ -488,20 +495,26 @@ __device__ void phase_msg_fast(const Ctx &c, int rel)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) { cc[rr][q] = dot4w(reinterpret_cast<const float(&)[4]>(w[q]), p.x, p.y, p.z, p.w, b[q]); acc[rr][q] = 0.f; }
                     }
+                    auto cell = [&](const float2 o) {
+                        float u[4];
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const int kn = min(32, n - 32 * t);        // warp-uniform
-                        for (int kk = 0; kk < kn; ++kk) {
-                            const float ox = __shfl_sync(0xffffffffu, my_o[t].x, kk), oy = __shfl_sync(0xffffffffu, my_o[t].y, kk);
-                            float u[4];
+                        for (int q = 0; q < 4; ++q) u[q] = fmaf(w[q][1], o.y, w[q][0] * o.x);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) u[q] = fmaf(w[q][1], oy, w[q][0] * ox);
+                        for (int rr = 0; rr < RC; ++rr)
 #pragma unroll
-                            for (int rr = 0; rr < RC; ++rr)
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) acc[rr][q] += fabsf(cc[rr][q] - u[q]);
-                        }
+                            for (int q = 0; q < 4; ++q) acc[rr][q] += fabsf(cc[rr][q] - u[q]);
+                    };
+                    int kk = 0;
+#pragma unroll 1
+                    for (; kk + 4 <= n; kk += 4) {                  // same k order as a plain loop: identical sums
+                        const float4 o01 = *reinterpret_cast<const float4 *>(so + kk), o23 = *reinterpret_cast<const float4 *>(so + kk + 2);
+                        cell(make_float2(o01.x, o01.y));
+                        cell(make_float2(o01.z, o01.w));
+                        cell(make_float2(o23.x, o23.y));
+                        cell(make_float2(o23.z, o23.w));
                     }
+#pragma unroll 1
+                    for (; kk < n; ++kk) cell(so[kk]);
 #pragma unroll
                     for (int rr = 0; rr < RC; ++rr) {
                         float o[4];
@@ -538,12 +551,19 @@ __device__ void phase_msg_fast(const Ctx &c, int rel)
                             bits = (idx >> 5) == 0 ? v0 : ((idx >> 5) == 1 ? v1 : ((idx >> 5) == 2 ? v2 : v3));
                         }
                         cnt += __popc(bits);
-                        while (bits) {                                                    // warp-uniform
-                            const int kk = __ffs(bits) - 1;
+                        while (bits) {                                                    // warp-uniform; two cells per trip, in bit order
+                            const int k0 = __ffs(bits) - 1;
                             bits &= bits - 1;
-                            const float ox = __shfl_sync(0xffffffffu, my_o[t].x, kk), oy = __shfl_sync(0xffffffffu, my_o[t].y, kk);
+                            const bool two = bits != 0u;
+                            const int k1 = two ? __ffs(bits) - 1 : k0;
+                            bits &= bits - 1;
+                            const float2 o0 = so[32 * t + k0], o1 = so[32 * t + k1];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) acc[q] += fmaxf(cc[q] - fmaf(w[q][1], oy, w[q][0] * ox), 0.f);
+                            for (int q = 0; q < 4; ++q) acc[q] += fmaxf(cc[q] - fmaf(w[q][1], o0.y, w[q][0] * o0.x), 0.f);
+                            if (two) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) acc[q] += fmaxf(cc[q] - fmaf(w[q][1], o1.y, w[q][0] * o1.x), 0.f);
+                            }
                         }
                     }
                     const float nrm = cnt ? 1.f / fmaxf((float)cnt, 1e-12f) : 0.f;
@@ -554,7 +574,7 @@ __device__ void phase_msg_fast(const Ctx &c, int rel)
     }
 }
 
-__device__ __forceinline__ bool fast_env_path(const StepArgs *a) { return (a->N == 4 || a->N == 8 || a->N == 16) && a->OW <= 8; }
+__device__ __forceinline__ bool fast_env_path(const StepArgs *a) { return (a->N == 4 || a->N == 8 || a->N == 16) && a->O <= OXY_CAP; }
 
 __device__ void phase_msg(const Ctx &c, int rel)
 {
@@ -841,6 +861,7 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
     static_assert(2 * NSTAGE + 3 <= 16, "barrier block");
     float4 *s_p = reinterpret_cast<float4 *>(bars + 16);                                  // 128 x float4 (later: s_val)
     float4 *s_e = s_p + ROWS;                                                               // 32 x float4
+    float2 *s_oxy = reinterpret_cast<float2 *>(smem + X_BYTES + NSTAGE * WSTAGE + MISC_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int net, tile;
     if (a.net_count == 2) { net = (int)blockIdx.x < a.n_tiles ? 1 : 0; tile = (int)blockIdx.x % a.n_tiles; }   // critic items first
@@ -869,7 +890,7 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
         // ================================================================================= workers
         Ctx c;
         c.a = &a; c.na = na; c.X = X; c.row0 = (int64_t)tile * a.rows_per_tile; c.warp = warp; c.lane = lane;
-        c.tmem = tmem_base; c.bar_a_ready = smem_u32(&bars[BAR_A_READY]); c.bar_mma_done = smem_u32(&bars[BAR_MMA_DONE]); c.group = 0; c.s_p = s_p; c.s_e = s_e; c.s_val = reinterpret_cast<float *>(s_p);
+        c.tmem = tmem_base; c.bar_a_ready = smem_u32(&bars[BAR_A_READY]); c.bar_mma_done = smem_u32(&bars[BAR_MMA_DONE]); c.group = 0; c.s_p = s_p; c.s_e = s_e; c.s_val = reinterpret_cast<float *>(s_p); c.s_oxy = s_oxy;
         {   // fp32 copies of the tile's pursuer / evader states (converted once; every SIMT phase reads them from smem)
             const int t = threadIdx.x;
             if (t < ROWS) {

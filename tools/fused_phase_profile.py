@@ -48,6 +48,8 @@ names = ["msg0", "msg1", "msg2", "epi_av(x3)", "epi_sem", "fcra", "epi_aggf", "e
 d = d[d[:, 12] > 0]            # CTAs that ran (critic items first, then the actor's)
 n_tiles = len(d) // 2
 print("items", len(d), "rows per tile ~", -(-B * N // max(n_tiles, 1)))
+tot = d[:, 12]
+print(f"per-item worker cycles: mean {tot.mean():.0f} min {tot.min():.0f} max {tot.max():.0f} std {tot.std():.0f}; sum/148 SMs = {tot.sum() / 148:.0f} cycles")
 for label, rows in (("critic", d[:n_tiles]), ("actor", d[n_tiles:])):
     print(label, "tiles", len(rows))
     for i, n in enumerate(names):
