@@ -908,6 +908,14 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
         for (int q = 0; q < 16; ++q) tk[q] = 0;
         long long t_prev = clock64();
         const long long t_begin = t_prev;
+        if (a.dbg && threadIdx.x == 0) {                            // profiling aid: wall-clock start (ns) and SM id of this CTA
+            unsigned long long gt;
+            unsigned smid;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            tk[13] = (long long)gt;
+            tk[15] = (long long)smid;
+        }
 #define PF_TICK(slot) do { const long long now_ = clock64(); tk[slot] += now_ - t_prev; t_prev = now_; } while (0)
         for (int r = 0; r < 3; ++r) {
             phase_msg(c, r);
@@ -959,6 +967,9 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
         }
         if (a.dbg && threadIdx.x == 0) {
             tk[12] = clock64() - t_begin;
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+            tk[14] = (long long)gt;
             for (int q = 0; q < 16; ++q) a.dbg[(size_t)blockIdx.x * 16 + q] = tk[q];
         }
     } else if (warp == 8) {

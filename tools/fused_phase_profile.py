@@ -43,6 +43,18 @@ for it in range(3):
     e.synchronize()
     print("launch ms", s.elapsed_time(e))
 d = dbg.cpu().numpy().astype(np.float64)
+# wall-clock schedule of the launch: effective SM clock, gaps between consecutive CTAs of one SM
+g0, g1, sm = d[:, 13], d[:, 14], d[:, 15].astype(int)
+ok = d[:, 12] > 0
+print(f"effective clock: {np.median(d[ok, 12] / (g1[ok] - g0[ok])):.3f} GHz; launch span {(g1[ok].max() - g0[ok].min()) / 1e3:.1f} us")
+gaps = []
+for s_ in np.unique(sm[ok]):
+    idx = np.where(ok & (sm == s_))[0]
+    idx = idx[np.argsort(g0[idx])]
+    gaps += list(g0[idx][1:] - g1[idx][:-1])
+    if s_ == 0:
+        print("SM 0 schedule (start us, dur us):", [(round((g0[i] - g0[ok].min()) / 1e3, 1), round((g1[i] - g0[i]) / 1e3, 1)) for i in idx])
+print(f"gap between consecutive CTAs on an SM: median {np.median(gaps) / 1e3:.2f} us, max {np.max(gaps) / 1e3:.2f} us; CTAs per SM: {ok.sum() / len(np.unique(sm[ok])):.2f}")
 names = ["msg0", "msg1", "msg2", "epi_av(x3)", "epi_sem", "fcra", "epi_aggf", "epi_f", "load_hidden(x2)", "epi_cell(x2)", "head",
          "wait_mma(all)", "total"]
 d = d[d[:, 12] > 0]            # CTAs that ran (critic items first, then the actor's)
