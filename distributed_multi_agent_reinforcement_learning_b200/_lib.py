@@ -110,6 +110,10 @@ _PROTOTYPES = {
     "marl_env3d_evader_step": (C.c_int, [_VP, _I32] + [_VP] * 4),
     "marl_env3d_adjacency": (C.c_int, [_VP, _I32] + [_VP] * 8),
     "marl_env3d_rollout": (C.c_int, [_VP, _I32, _I32, _I32, _I32] + [_VP] * 8 + [_U64, _VP, _VP]),
+    "marl_envn2n_step": (C.c_int, [_VP, _I32] + [_VP] * 10),
+    "marl_envn2n_evader_step": (C.c_int, [_VP, _I32] + [_VP] * 4),
+    "marl_envn2n_observe": (C.c_int, [_VP, _I32] + [_VP] * 8),
+    "marl_envn2n_rollout": (C.c_int, [_VP, _I32, _I32, _I32, _I32] + [_VP] * 8 + [_U64, _VP, _VP]),
     "marl_rollout_steps": (C.c_int, [_PP, _I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _U64, _VP, _VP, _VP, _VP, _VP,
                                      _VP, _VP, _VP, _VP, _VP, C.POINTER(RolloutRecords), _VP]),
 }

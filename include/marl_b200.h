@@ -271,6 +271,55 @@ int marl_env3d_rollout(const marl_env3d_params *p, int32_t B, int32_t T, int32_t
                        int32_t *d_time_step, const double *d_action_tape, const double *d_e_action_tape, uint64_t seed,
                        const marl_env3d_records *rec, void *stream);
 
+/* ---- third env family: 2-D N-pursuers-vs-E-evaders particle env (environment/env_n2n/particle_env.py) ----------------------
+ * State: pursuers f64 [B,N,4] = (x, y, phi, v), evaders f64 [B,E,4], active u8 [B,N] / [B,E], target f64 [B,2], time_step i32 [B].
+ * N, E <= 32.  Pursuers take the discrete heading actions 0..8 (0 = stop), evaders a commanded heading in [-1,1] (the reference's
+ * SLSQP evader `eva.e_f` is third-party arithmetic: its output is an input here).
+ * marl_envn2n_step        = ParticleEnv.step (:164-177): Pursuer.step of every pursuer (an inactive one still turns, :34-63), reward
+ *                           (:263-285), update_agent_active (:287-321, parked at (1000,1000), phi 0), get_done (:248-262) / episode_limit.
+ * marl_envn2n_evader_step = the Evader.step half of evader_step (:179-193, :70-93) for commanded headings d_e_action f64 [B,E].
+ * marl_envn2n_observe     = get_adj_mat (:338-350) for pursuer-pursuer (comm_range) and pursuer-evader (sen_range) as one word per
+ *                           pursuer (bit j = column j; rows of inactive pursuers are zero) and choose_evader('actor') (:392-420) as the
+ *                           index of the chosen evader or -1.
+ * marl_envn2n_rollout     = K fused iterations of (observe -> evader move -> step -> store) with actions from tapes (d_action_tape i32
+ *                           [K,B,N], d_e_action_tape f64 [K,B,E]) or, when a tape is NULL, from the counter RNG.  Time-major records
+ *                           (any may be NULL): states / active flags BEFORE the step, observations, actions, rewards, done. */
+typedef struct marl_envn2n_params {
+    int32_t N, E;              /* p_num, e_num */
+    int32_t episode_limit;     /* 100 */
+    int32_t reserved;
+    double p_vmax;             /* 0.3 (the evaders' speed is part of their state) */
+    double kill_radius;        /* 0.5 */
+    double ang_lmt;            /* pi/4 */
+    double step_size;          /* 0.5 */
+    double comm_range;         /* p_comm_range 6 */
+    double sen_range;          /* p_sen_range 3 */
+} marl_envn2n_params;
+typedef struct marl_envn2n_records {
+    float *p_state_f32;        /* [T,B,N,4] */
+    float *e_state_f32;        /* [T,B,E,4] */
+    uint8_t *p_active;         /* [T,B,N] */
+    uint8_t *e_active;         /* [T,B,E] */
+    uint32_t *pp_adj_bits;     /* [T,B,N] */
+    uint32_t *pe_adj_bits;     /* [T,B,N] */
+    int8_t *assign;            /* [T,B,N] */
+    int32_t *action;           /* [T,B,N] */
+    int32_t *reward;           /* [T,B,N] */
+    uint8_t *done;             /* [T,B] */
+} marl_envn2n_records;
+int marl_envn2n_step(const marl_envn2n_params *p, int32_t B, double *d_p_state, uint8_t *d_p_active, double *d_e_state,
+                     uint8_t *d_e_active, const double *d_target, const int32_t *d_action, int32_t *d_time_step,
+                     int32_t *d_reward, uint8_t *d_done, void *stream);
+int marl_envn2n_evader_step(const marl_envn2n_params *p, int32_t B, double *d_e_state, uint8_t *d_e_active,
+                            const double *d_e_action, void *stream);
+int marl_envn2n_observe(const marl_envn2n_params *p, int32_t B, const double *d_p_state, const uint8_t *d_p_active,
+                        const double *d_e_state, const uint8_t *d_e_active, uint32_t *d_pp_adj_bits, uint32_t *d_pe_adj_bits,
+                        int8_t *d_assign, void *stream);
+int marl_envn2n_rollout(const marl_envn2n_params *p, int32_t B, int32_t T, int32_t t0, int32_t K, double *d_p_state,
+                        uint8_t *d_p_active, double *d_e_state, uint8_t *d_e_active, const double *d_target,
+                        int32_t *d_time_step, const int32_t *d_action_tape, const double *d_e_action_tape, uint64_t seed,
+                        const marl_envn2n_records *rec, void *stream);
+
 /* ---- kernel family 5: DHGN actor/critic, the non-GEMM parts (fp32) -----------------------------------------
  * The dense E-wide layers (AGG_vertex_0, semantic_layer, AGG_fcra_k, FCRA_layers.k, GRU weight matrices) are plain
  * library GEMMs on the host side; these entry points fuse everything pairwise / sparse / pointwise around them so that
@@ -361,7 +410,7 @@ typedef struct marl_policy_step {
     float *d_value;              /* [B,N] out (critic) */
     void *d_debug;               /* NULL, or i64 [grid,16] per-CTA phase cycle counters (profiling aid) */
 } marl_policy_step;
-/* Pre-splits (hi/lo TF32) and pre-swizzles every dense layer of one network into the shared-memory image the fused kernel
+/* Pre-splits (two-term fp16: hi = fp16(w), lo = fp16(w - hi)) and pre-swizzles every dense layer of one network into the shared-memory image the fused kernel
  * streams; call once per weight update. */
 int64_t marl_policy_pack_bytes(int32_t depth, int32_t is_actor);
 int marl_policy_pack(const marl_dhgn_weights *w, int32_t depth, int32_t is_actor, int32_t action_dim, void *d_packed, void *stream);
