@@ -13,14 +13,16 @@
 // (marl_policy_pack) into the exact shared-memory image of each k-block, so that the producer is a single elected thread
 // issuing cp.async.bulk copies (32 KB per stage) that complete on an mbarrier.
 //
-// CTA = one (row tile, network) work item, 10 warps:
-//   warps 0-7  workers: SIMT phases (messages, FCRA neighbour mean, hidden-state load) that write the activation tile X
+// CTA = one (row tile, network) work item, WW + 2 warps (WW = 16 worker warps, or 8 for 16-agent envs - see Lay<WW>):
+//   warps 0..WW-1  workers: SIMT phases (messages, FCRA neighbour mean, hidden-state load) that write the activation tile X
 //              straight into the canonical K-major SWIZZLE_128B operand layout (hi and lo planes), and the epilogues
-//              (tcgen05.ld -> bias / ReLU / GRU cell / heads -> X again, plus the few global stores);
-//   warp 8     weight loader (elected lane): streams the packed units through a 4-stage ring;
-//   warp 9     MMA issuer (elected lane) + TMEM allocation (all 512 columns: the GRU needs four 128-column accumulators).
+//              (tcgen05.ld -> bias / ReLU / GRU cell / heads -> X again, plus the few global stores).  These phases are
+//              latency-bound (dependent FMA / MUFU chains, shared-memory round trips): 16 warps at 96 registers run them
+//              ~1.4x faster than 8 warps at 168;
+//   warp WW    weight loader (elected lane): streams the packed units through a 4-stage ring;
+//   warp WW+1  MMA issuer (elected lane) + TMEM allocation (all 512 columns: the GRU needs four 128-column accumulators).
 // Workers and the issuer follow the same static unit program and hand the tile back and forth with two mbarriers
-// (a_ready: 256 arrivals, mma_done: tcgen05.commit).
+// (a_ready: one arrival per worker thread, mma_done: tcgen05.commit).
 // Shared memory: X 64 KB (2 k-blocks of K = 64 x (hi 16 KB + lo 16 KB)) + 4 x 32 KB weight stages.
 #include "common.cuh"
 #include <cuda_fp16.h>
@@ -36,9 +38,18 @@ constexpr int X_BYTES = NKB * XKB;        // K = 128
 constexpr int WSTAGE = 2 * TILE;          // one k-block of a 128-row weight unit: hi + lo
 constexpr int MISC_BYTES = 3072;           // barriers, fp32 state of the tile
 constexpr int OXY_CAP = 256;               // boundary cells of one map staged per worker warp (fast message path: O <= 256)
-constexpr int OXY_BYTES = 8 * OXY_CAP * 8; // 8 worker warps x 256 float2
-constexpr int SMEM_BYTES = X_BYTES + NSTAGE * WSTAGE + MISC_BYTES + OXY_BYTES;   // 211 KB
-constexpr int WORKERS = 256, THREADS = 320;
+constexpr int OXY_BYTES = 16 * OXY_CAP * 8; // up to 16 worker warps x 256 float2
+constexpr int SMEM_BYTES = X_BYTES + NSTAGE * WSTAGE + MISC_BYTES + OXY_BYTES;   // 227 KB
+// Worker-warp count WW is a template parameter of the kernel: 16 worker warps (8 rows each in the SIMT phases, 32 columns each in
+// the epilogues) when an env fits in 8 rows - the SIMT phases are latency-bound, twice the warps hide twice the latency - and 8
+// worker warps (16 rows / 64 columns each) for N = 16, whose env-grouped message path needs a whole env per warp.
+template <int WW>
+struct Lay {
+    static_assert(WW == 8 || WW == 16, "8 or 16 worker warps");
+    static constexpr int RPW = ROWS / WW;            // rows per warp in the SIMT phases
+    static constexpr int CPT = 128 / (WW / 4);       // accumulator columns per thread in the epilogues
+    static constexpr int WORKERS = WW * 32, THREADS = (WW + 2) * 32;
+};
 
 struct Unit {
     uint32_t off;        // byte offset of the packed unit
@@ -233,7 +244,7 @@ struct Ctx {
     int group;           // groups completed so far (parity of mma_done)
     float4 *s_p;         // [128] fp32 pursuer state of the tile's rows (converted once)
     float4 *s_e;         // [32] fp32 evader state of the tile's envs (when the tile has <= 32 envs)
-    float *s_val;        // [2][128] scratch for the critic value (aliases s_p, which is dead by then)
+    float *s_val;        // [WW/4][128] scratch for the critic value (aliases s_p, which is dead by then)
     float2 *s_oxy;       // [8 warps][OXY_CAP] boundary cells of the env a warp is working on (obstacle relation)
 };
 
@@ -265,7 +276,8 @@ __device__ __forceinline__ float dot4w(const float (&w)[4], float a0, float a1, 
 {
     return fmaf(w[3], a3, fmaf(w[2], a2, fmaf(w[1], a1, fmaf(w[0], a0, 0.f)))) + b;
 }
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int WW>
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(WW * 32) : "memory"); }
 
 // workers: hand X to the issuer (signal_ready), then wait until the group's MMAs have completed (wait_done).  Work that does not
 // touch X or TMEM — global loads of the NEXT phase's operands — goes between the two, so that its latency hides behind the MMAs.
@@ -314,16 +326,18 @@ __device__ __forceinline__ void load_msg_weights(const NetArgs *na, int rel, int
 
 // ---- DHGN.message + mean aggregation, generic per-row path (any N) -> X ----------------------------------------------------
 // Same arithmetic as msg_agg_fwd_kernel (policy_kernels.cu).  lane l owns channels 4l..4l+3.
+template <int WW>
 __device__ void phase_msg_generic(const Ctx &c, int rel)
 {
+    constexpr int RPW = Lay<WW>::RPW;
     const StepArgs *a = c.a;
     const NetArgs *na = c.na;
     const int lane = c.lane, N = a->N;
     float w[4][8], b[4];
     load_msg_weights(na, rel, lane, w, b);
 #pragma unroll 1
-    for (int rr = 0; rr < 16; ++rr) {
-        const int r = 16 * c.warp + rr;
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int r = RPW * c.warp + rr;
         int64_t gr;
         int env, i;
         const bool ok = row_info(c, r, gr, env, i);
@@ -398,9 +412,11 @@ __device__ void phase_msg_generic(const Ctx &c, int rel)
 //   relation 2, critic (all cells of the map): sum_k relu(cc_i - u_k) = ((n cc_i - sum_k u_k) + sum_k |cc_i - u_k|) / 2 with
 //               cc_i = W2 p_i + b2, u_k = W2[:, :2] o_k                    (2 instructions per (i, k, channel));
 //   the map's boundary cells live in registers (lane l holds cells l, l+32, ...) and are broadcast with shuffles.
-template <int NA>
+template <int NA, int WW>
 __device__ void phase_msg_fast(const Ctx &c, int rel)
 {
+    constexpr int RPW = Lay<WW>::RPW;
+    static_assert(RPW % NA == 0, "whole envs per warp");
     const StepArgs *a = c.a;
     const NetArgs *na = c.na;
     const int lane = c.lane;
@@ -408,8 +424,8 @@ __device__ void phase_msg_fast(const Ctx &c, int rel)
     load_msg_weights(na, rel, lane, w, b);
     constexpr int RC = NA < 8 ? NA : 8;      // rows per register chunk of the critic's obstacle relation
 #pragma unroll 1
-    for (int g = 0; g < 16 / NA; ++g) {
-        const int r0 = 16 * c.warp + g * NA;
+    for (int g = 0; g < RPW / NA; ++g) {
+        const int r0 = RPW * c.warp + g * NA;
         int64_t gr0;
         int env, i0;
         const bool ok = row_info(c, r0, gr0, env, i0);     // rows of an env are valid together
@@ -574,26 +590,33 @@ __device__ void phase_msg_fast(const Ctx &c, int rel)
     }
 }
 
-__device__ __forceinline__ bool fast_env_path(const StepArgs *a) { return (a->N == 4 || a->N == 8 || a->N == 16) && a->O <= OXY_CAP; }
+template <int WW>
+__device__ __forceinline__ bool fast_env_path(const StepArgs *a)
+{
+    return (a->N == 4 || a->N == 8 || a->N == 16) && a->N <= Lay<WW>::RPW && a->O <= OXY_CAP;
+}
 
+template <int WW>
 __device__ void phase_msg(const Ctx &c, int rel)
 {
-    if (!fast_env_path(c.a)) phase_msg_generic(c, rel);
-    else if (c.a->N == 8) phase_msg_fast<8>(c, rel);
-    else if (c.a->N == 16) phase_msg_fast<16>(c, rel);
-    else phase_msg_fast<4>(c, rel);
+    if (!fast_env_path<WW>(c.a)) phase_msg_generic<WW>(c, rel);
+    else if (c.a->N == 8) phase_msg_fast<8, WW>(c, rel);
+    else if (c.a->N == 4) phase_msg_fast<4, WW>(c, rel);
+    else if constexpr (WW == 8) phase_msg_fast<16, WW>(c, rel);
 }
 
 // ---- DHGN.fcra neighbour mean of the k-th history embedding -> X --------------------------------------------------------
+template <int WW>
 __device__ void phase_fcra_generic(const Ctx &c, int k)
 {
+    constexpr int RPW = Lay<WW>::RPW;
     const StepArgs *a = c.a;
     const NetArgs *na = c.na;
     const float *hist = na->hist[k];
     const int N = a->N;
 #pragma unroll 1
-    for (int rr = 0; rr < 16; ++rr) {
-        const int r = 16 * c.warp + rr;
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int r = RPW * c.warp + rr;
         int64_t gr;
         int env, i;
         const bool ok = row_info(c, r, gr, env, i);
@@ -616,15 +639,16 @@ __device__ void phase_fcra_generic(const Ctx &c, int k)
 
 // env-grouped path, split in two: the history rows of the warp's envs are fetched (16 independent 512-byte warp loads, issued
 // while the previous MMA group runs) and then averaged per row from registers
-template <int NA>
-__device__ __forceinline__ void fcra_prefetch(const Ctx &c, int k, float4 (&h)[16], uint32_t (&words)[4])
+template <int NA, int WW>
+__device__ __forceinline__ void fcra_prefetch(const Ctx &c, int k, float4 (&h)[Lay<WW>::RPW], uint32_t (&words)[4])
 {
+    constexpr int RPW = Lay<WW>::RPW;
     const StepArgs *a = c.a;
     const NetArgs *na = c.na;
     const float *hist = na->hist[k];
 #pragma unroll
-    for (int g = 0; g < 16 / NA; ++g) {
-        const int r0 = 16 * c.warp + g * NA;
+    for (int g = 0; g < RPW / NA; ++g) {
+        const int r0 = RPW * c.warp + g * NA;
         int64_t gr0;
         int env, i0;
         const bool ok = row_info(c, r0, gr0, env, i0);
@@ -634,12 +658,13 @@ __device__ __forceinline__ void fcra_prefetch(const Ctx &c, int k, float4 (&h)[1
             h[g * NA + j] = (ok && hist) ? __ldg(reinterpret_cast<const float4 *>(hist + (gr0 + j) * E) + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
-template <int NA>
-__device__ __forceinline__ void fcra_finish(const Ctx &c, const float4 (&h)[16], const uint32_t (&words)[4])
+template <int NA, int WW>
+__device__ __forceinline__ void fcra_finish(const Ctx &c, const float4 (&h)[Lay<WW>::RPW], const uint32_t (&words)[4])
 {
+    constexpr int RPW = Lay<WW>::RPW;
 #pragma unroll
-    for (int g = 0; g < 16 / NA; ++g) {
-        const int r0 = 16 * c.warp + g * NA;
+    for (int g = 0; g < RPW / NA; ++g) {
+        const int r0 = RPW * c.warp + g * NA;
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
             const uint32_t word = __shfl_sync(0xffffffffu, words[g], i);
@@ -656,45 +681,53 @@ __device__ __forceinline__ void fcra_finish(const Ctx &c, const float4 (&h)[16],
         }
     }
 }
-__device__ __forceinline__ void phase_fcra_prefetch(const Ctx &c, int k, float4 (&h)[16], uint32_t (&words)[4])
+template <int WW>
+__device__ __forceinline__ void phase_fcra_prefetch(const Ctx &c, int k, float4 (&h)[Lay<WW>::RPW], uint32_t (&words)[4])
 {
-    if (!fast_env_path(c.a)) return;
-    if (c.a->N == 8) fcra_prefetch<8>(c, k, h, words);
-    else if (c.a->N == 16) fcra_prefetch<16>(c, k, h, words);
-    else fcra_prefetch<4>(c, k, h, words);
+    if (!fast_env_path<WW>(c.a)) return;
+    if (c.a->N == 8) fcra_prefetch<8, WW>(c, k, h, words);
+    else if (c.a->N == 4) fcra_prefetch<4, WW>(c, k, h, words);
+    else if constexpr (WW == 8) fcra_prefetch<16, WW>(c, k, h, words);
 }
-__device__ __forceinline__ void phase_fcra_finish(const Ctx &c, int k, const float4 (&h)[16], const uint32_t (&words)[4])
+template <int WW>
+__device__ __forceinline__ void phase_fcra_finish(const Ctx &c, int k, const float4 (&h)[Lay<WW>::RPW], const uint32_t (&words)[4])
 {
-    if (!fast_env_path(c.a)) phase_fcra_generic(c, k);
-    else if (c.a->N == 8) fcra_finish<8>(c, h, words);
-    else if (c.a->N == 16) fcra_finish<16>(c, h, words);
-    else fcra_finish<4>(c, h, words);
+    if (!fast_env_path<WW>(c.a)) phase_fcra_generic<WW>(c, k);
+    else if (c.a->N == 8) fcra_finish<8, WW>(c, h, words);
+    else if (c.a->N == 4) fcra_finish<4, WW>(c, h, words);
+    else if constexpr (WW == 8) fcra_finish<16, WW>(c, h, words);
 }
 
 // ---- previous hidden state of GRU layer l -> X (16 independent 512-byte warp loads in flight) ----------------------------
-__device__ __forceinline__ void hidden_prefetch(const Ctx &c, int l, float4 (&v)[16])
+template <int WW>
+__device__ __forceinline__ void hidden_prefetch(const Ctx &c, int l, float4 (&v)[Lay<WW>::RPW])
 {
+    constexpr int RPW = Lay<WW>::RPW;
     const float *h = c.na->hidden + (int64_t)l * c.a->R * E;
 #pragma unroll
-    for (int rr = 0; rr < 16; ++rr) {
+    for (int rr = 0; rr < RPW; ++rr) {
         int64_t gr;
         int env, i;
-        const bool ok = row_info(c, 16 * c.warp + rr, gr, env, i);
+        const bool ok = row_info(c, RPW * c.warp + rr, gr, env, i);
         v[rr] = ok ? *(reinterpret_cast<const float4 *>(h + gr * E) + c.lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
-__device__ __forceinline__ void hidden_store(const Ctx &c, const float4 (&v)[16])
+template <int WW>
+__device__ __forceinline__ void hidden_store(const Ctx &c, const float4 (&v)[Lay<WW>::RPW])
 {
+    constexpr int RPW = Lay<WW>::RPW;
 #pragma unroll
-    for (int rr = 0; rr < 16; ++rr) x_store4(c.X, 16 * c.warp + rr, c.lane, v[rr]);
+    for (int rr = 0; rr < RPW; ++rr) x_store4(c.X, RPW * c.warp + rr, c.lane, v[rr]);
 }
 
-// X (hi + lo: fp32 to one ulp) -> global rows, coalesced: warp w copies rows 16w..16w+15, 512 bytes per row
+// X (hi + lo: fp32 to one ulp) -> global rows, coalesced: warp w copies its RPW rows, 512 bytes per row
+template <int WW>
 __device__ void copy_out(const Ctx &c, float *g)
 {
+    constexpr int RPW = Lay<WW>::RPW;
 #pragma unroll 4
-    for (int rr = 0; rr < 16; ++rr) {
-        const int r = 16 * c.warp + rr;
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int r = RPW * c.warp + rr;
         int64_t gr;
         int env, i;
         if (row_info(c, r, gr, env, i)) *(reinterpret_cast<float4 *>(g + gr * E) + c.lane) = x_load4(c.X, r, c.lane);
@@ -702,15 +735,17 @@ __device__ void copy_out(const Ctx &c, float *g)
 }
 
 // ---- epilogue: X <- act(acc + bias [+ W_p p_i]) ; optional global copy ---------------------------------------------------
-// thread <-> row 32*(warp&3)+lane (its TMEM lane), columns [64*(warp>>2), +64)
+// thread <-> row 32*(warp&3)+lane (its TMEM lane), columns [CPT*(warp>>2), +CPT)
+template <int WW>
 __device__ void epi_store(const Ctx &c, int acc_col, const float *bias, bool relu, const float *wp, int wp_ld, float *gout)
 {
+    constexpr int CPT = Lay<WW>::CPT;
     const int row = 32 * (c.warp & 3) + c.lane, hh = c.warp >> 2;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (wp) p = c.s_p[row];
     const uint32_t taddr = c.tmem + ((uint32_t)(32 * (c.warp & 3)) << 16) + (uint32_t)acc_col;
 #pragma unroll 1
-    for (int c0 = 64 * hh; c0 < 64 * hh + 64; c0 += 32) {
+    for (int c0 = CPT * hh; c0 < CPT * hh + CPT; c0 += 32) {
         uint32_t v[32];
         PF_TMEM_LD32(v, taddr + (uint32_t)c0);
         tmem_wait_ld();
@@ -735,8 +770,8 @@ __device__ void epi_store(const Ctx &c, int acc_col, const float *bias, bool rel
         }
     }
     if (gout) {
-        worker_sync();
-        copy_out(c, gout);
+        worker_sync<WW>();
+        copy_out<WW>(c, gout);
     }
 }
 
@@ -746,15 +781,17 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.
 // ---- epilogue: GRU cell of layer l (torch gate order r, z, n); h' -> X (then coalesced to global); critic layer 1: value ---
 // h_prev is read back from X (it is the A operand of the W_hh group; hi + lo = fp32 to one ulp).  The gates use ex2-based exp and the fast
 // division (abs error ~1e-7, inside the 1e-5 forward tolerance).
+template <int WW>
 __device__ void epi_cell(const Ctx &c, int l, bool want_value)
 {
+    constexpr int CPT = Lay<WW>::CPT;
     const NetArgs *na = c.na;
     const int row = 32 * (c.warp & 3) + c.lane, hh = c.warp >> 2;
     const float *bi = na->b_ih[l], *bh = na->b_hh[l];
     const uint32_t taddr = c.tmem + ((uint32_t)(32 * (c.warp & 3)) << 16);
     float vdot = 0.f;
 #pragma unroll 1
-    for (int c0 = 64 * hh; c0 < 64 * hh + 64; c0 += 16) {
+    for (int c0 = CPT * hh; c0 < CPT * hh + CPT; c0 += 16) {
         uint32_t ar[16], az[16], an[16], ahn[16];
         PF_TMEM_LD16(ar, taddr + (uint32_t)c0);
         PF_TMEM_LD16(az, taddr + (uint32_t)(128 + c0));
@@ -795,12 +832,16 @@ __device__ void epi_cell(const Ctx &c, int l, bool want_value)
         for (int j = 0; j < 16; j += 8) x_store8(c.X, row, (c0 + j) >> 3, hn_all[j >> 3]);
     }
     if (want_value) c.s_val[hh * ROWS + row] = vdot;
-    worker_sync();
-    copy_out(c, na->hidden + (int64_t)l * c.a->R * E);
+    worker_sync<WW>();
+    copy_out<WW>(c, na->hidden + (int64_t)l * c.a->R * E);
     if (want_value && hh == 0 && c.a->value) {
         int64_t gr;
         int env, i;
-        if (row_info(c, row, gr, env, i)) c.a->value[gr] = (c.s_val[row] + c.s_val[ROWS + row]) + __ldg(na->head_b);
+        if (row_info(c, row, gr, env, i)) {
+            float v = c.s_val[row] + c.s_val[ROWS + row];
+            if (WW == 16) v = (v + c.s_val[2 * ROWS + row]) + c.s_val[3 * ROWS + row];
+            c.a->value[gr] = v + __ldg(na->head_b);
+        }
     }
 }
 
@@ -849,9 +890,11 @@ __device__ void epi_head(const Ctx &c)
     if (c.a->logp) c.a->logp[gr] = lpa;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <int WW>
+__global__ void __launch_bounds__(Lay<WW>::THREADS, 1)
 policy_step_kernel(const __grid_constant__ StepArgs a)
 {
+    constexpr int RPW = Lay<WW>::RPW;
     extern __shared__ __align__(1024) unsigned char smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();          // SWIZZLE_128B atoms need 1024-byte alignment
     unsigned char *X = smem;
@@ -873,11 +916,11 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
             mbar_init(smem_u32(&bars[s]), 1);            // full: one arrive.expect_tx + the bulk copy's bytes
             mbar_init(smem_u32(&bars[NSTAGE + s]), 1);   // empty: one tcgen05.commit
         }
-        mbar_init(smem_u32(&bars[BAR_A_READY]), WORKERS);   // a_ready
+        mbar_init(smem_u32(&bars[BAR_A_READY]), Lay<WW>::WORKERS);   // a_ready
         mbar_init(smem_u32(&bars[BAR_MMA_DONE]), 1);        // mma_done
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {
+    if (warp == WW + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -886,7 +929,7 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
+    if (warp < WW) {
         // ================================================================================= workers
         Ctx c;
         c.a = &a; c.na = na; c.X = X; c.row0 = (int64_t)tile * a.rows_per_tile; c.warp = warp; c.lane = lane;
@@ -901,7 +944,7 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
                 const int64_t env = c.row0 / a.N + (t - ROWS);
                 s_e[t - ROWS] = (ROWS / a.N <= 32 && t - ROWS < ROWS / a.N && env < a.B) ? load_e(&a, (int)env) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            worker_sync();
+            worker_sync<WW>();
         }
         long long tk[16];
 #pragma unroll
@@ -918,45 +961,45 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
         }
 #define PF_TICK(slot) do { const long long now_ = clock64(); tk[slot] += now_ - t_prev; t_prev = now_; } while (0)
         for (int r = 0; r < 3; ++r) {
-            phase_msg(c, r);
+            phase_msg<WW>(c, r);
             PF_TICK(0 + r);
             hand_over(c);                                              // AGG_vertex_0 -> acc @0
             PF_TICK(11);
-            epi_store(c, 0, na->b_av, true, nullptr, 0, nullptr);
+            epi_store<WW>(c, 0, na->b_av, true, nullptr, 0, nullptr);
             PF_TICK(3);
             hand_over(c);                                              // semantic, K-slice r -> acc @128
             PF_TICK(11);
         }
-        epi_store(c, 128, na->b_sem, false, na->sem_w, na->sem_ld, nullptr);    // h0 (no activation)
+        epi_store<WW>(c, 128, na->b_sem, false, na->sem_w, na->sem_ld, nullptr);    // h0 (no activation)
         PF_TICK(4);
-        float4 pre[16];
+        float4 pre[RPW];
         for (int k = 0; k < a.depth; ++k) {
             uint32_t words[4] = {0u, 0u, 0u, 0u};
             signal_ready(c);                                           // FCRA_k, h part -> acc @128
-            phase_fcra_prefetch(c, k, pre, words);                     //   ... while it runs: the history rows of the tile
+            phase_fcra_prefetch<WW>(c, k, pre, words);                     //   ... while it runs: the history rows of the tile
             wait_done(c);
             PF_TICK(11);
-            phase_fcra_finish(c, k, pre, words);
+            phase_fcra_finish<WW>(c, k, pre, words);
             PF_TICK(5);
             hand_over(c);                                              // AGG_fcra_k -> acc @0
             PF_TICK(11);
-            epi_store(c, 0, na->b_aggf[k], true, nullptr, 0, nullptr);
+            epi_store<WW>(c, 0, na->b_aggf[k], true, nullptr, 0, nullptr);
             PF_TICK(6);
             hand_over(c);                                              // FCRA_k, m part -> acc @128 (+=)
             PF_TICK(11);
-            epi_store(c, 128, na->b_f[k], true, nullptr, 0, k == a.depth - 1 ? na->emb_out : nullptr);
+            epi_store<WW>(c, 128, na->b_f[k], true, nullptr, 0, k == a.depth - 1 ? na->emb_out : nullptr);
             PF_TICK(7);
         }
         for (int l = 0; l < 2; ++l) {
             signal_ready(c);                                           // W_ih: r @0, z @128, n @256
-            hidden_prefetch(c, l, pre);                                //   ... while it runs: h_prev of this layer
+            hidden_prefetch<WW>(c, l, pre);                                //   ... while it runs: h_prev of this layer
             wait_done(c);
             PF_TICK(11);
-            hidden_store(c, pre);
+            hidden_store<WW>(c, pre);
             PF_TICK(8);
             hand_over(c);                                              // W_hh: r += , z +=, hn @384
             PF_TICK(11);
-            epi_cell(c, l, l == 1 && na->head_w_eff != nullptr);
+            epi_cell<WW>(c, l, l == 1 && na->head_w_eff != nullptr);
             PF_TICK(9);
         }
         if (net == 0) {
@@ -972,7 +1015,7 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
             tk[14] = (long long)gt;
             for (int q = 0; q < 16; ++q) a.dbg[(size_t)blockIdx.x * 16 + q] = tk[q];
         }
-    } else if (warp == 8) {
+    } else if (warp == WW) {
         // ================================================================================= weight loader
         if (lane == 0) {
             int it = 0;
@@ -1028,7 +1071,7 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (warp == WW + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 // ---- weight packing: one unit = W[rows, k0 : k0+128] -> 2 k-blocks (K = 64) x (hi plane, lo plane) in the smem image ------------
@@ -1205,8 +1248,12 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
     const bool both = actor_w && actor_io && critic_w && critic_io;
     a.net_count = both ? 2 : 1;
     a.net_first = (actor_w && actor_io) ? 0 : 1;
-    cudaError_t e = cudaFuncSetAttribute(pf::policy_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pf::SMEM_BYTES);
+    // 16 worker warps unless the env-grouped message path needs a whole 16-agent env per warp
+    const bool wide = !(s->N == 16 && s->O <= pf::OXY_CAP);
+    cudaError_t e = wide ? cudaFuncSetAttribute(pf::policy_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, pf::SMEM_BYTES)
+                         : cudaFuncSetAttribute(pf::policy_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, pf::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("policy_step_kernel: smem %d: %s", pf::SMEM_BYTES, cudaGetErrorString(e)); return MARL_ECUDA; }
-    pf::policy_step_kernel<<<a.n_tiles * a.net_count, pf::THREADS, pf::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    if (wide) pf::policy_step_kernel<16><<<a.n_tiles * a.net_count, pf::Lay<16>::THREADS, pf::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    else pf::policy_step_kernel<8><<<a.n_tiles * a.net_count, pf::Lay<8>::THREADS, pf::SMEM_BYTES, (cudaStream_t)stream>>>(a);
     return check_launch("policy_step_kernel");
 }

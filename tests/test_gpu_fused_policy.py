@@ -73,7 +73,7 @@ def test_fused_step_reproduces_reference_rollout_buffer(path):
         torch.testing.assert_close(logp, cu(fx["a_logprob_n"][:, t]), **tol)
 
 
-@pytest.mark.parametrize("B,N,D,steps", [(300, 8, 1, 4), (70, 5, 3, 5), (9, 16, 2, 3), (7, 20, 1, 2)])
+@pytest.mark.parametrize("B,N,D,steps", [(300, 8, 1, 4), (70, 5, 3, 5), (9, 16, 2, 3), (7, 20, 1, 2), (45, 4, 1, 3)])
 def test_fused_step_matches_unfused_kernels(B, N, D, steps):
     from distributed_multi_agent_reinforcement_learning_b200 import policy_ops as ops
     from distributed_multi_agent_reinforcement_learning_b200.fused_policy import FusedRolloutStep
