@@ -487,11 +487,12 @@ def run_ours(args):
     # HBM traffic the fused kernel needs per launch: state/adjacency in, history in, embedding + hidden (r/w) + heads out
     bytes_launch = B * N * (32 + 4 + 1 + 24 + 2 * (cfg.algo.depth * 512 + 512 + 4 * 512) + 12)
     roofline = {"kernel": "policy_step_kernel (DHGN encoder + 2-layer GRU + heads of actor AND critic, one launch per env step; "
-                          "tcgen05 kind::tf32, 3xTF32 split for fp32-level accuracy, accumulators in TMEM)",
+                          "tcgen05 kind::f16 on a two-term fp16 split of both operands, 3 products per K step for fp32-level accuracy, "
+                          "accumulators in TMEM)",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                "traffic": 153.5e6, "traffic_source": "profiles/r1_policy_step_kernel_ncu_summary.txt (dram read + write of one launch, ncu --set full)",
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16; kind::tf32 runs at half of it "
-                                                "and the 3xTF32 split issues 3 MMAs per product, so this kernel's ceiling is frac = 1/6)",
+                "traffic": 144.9e6, "traffic_source": "profiles/r1_policy_step_kernel_ncu_summary.txt (dram read + write of one launch, ncu --set full)",
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16 = the kind::f16 rate; the split issues 3 MMAs "
+                               "per algorithmic product, so this kernel's ceiling is frac = 1/3)",
                 "algorithmic_flops_per_launch": flops_launch, "flops_per_agent_per_network": policy_flops_per_agent(N, env.O, cfg.algo.depth),
                 "avg_launch_us": pk["avg_us"], "share_of_step": pk["total_ms"] / ms_episode,
                 "hbm_bytes_per_launch_algorithmic": bytes_launch,
