@@ -73,7 +73,8 @@ struct NetArgs {
     const float *head_w_eff;   // critic: effective [E] row (fp32); actor: unused
     const float *hist[MAXD];   // [B,N,E] history embeddings, k = 0 most recent; null = zeros
     float *emb_out;            // [B,N,E]
-    float *hidden;             // [2, R, E] in/out
+    const float *hidden_in;    // [2, R, E] previous hidden state
+    float *hidden_out;         // [2, R, E] new hidden state (may alias hidden_in in the one-CTA-per-SM kernel)
     int all_ones;              // critic
 };
 
@@ -703,7 +704,7 @@ template <int WW>
 __device__ __forceinline__ void hidden_prefetch(const Ctx &c, int l, float4 (&v)[Lay<WW>::RPW])
 {
     constexpr int RPW = Lay<WW>::RPW;
-    const float *h = c.na->hidden + (int64_t)l * c.a->R * E;
+    const float *h = c.na->hidden_in + (int64_t)l * c.a->R * E;
 #pragma unroll
     for (int rr = 0; rr < RPW; ++rr) {
         int64_t gr;
@@ -833,7 +834,7 @@ __device__ void epi_cell(const Ctx &c, int l, bool want_value)
     }
     if (want_value) c.s_val[hh * ROWS + row] = vdot;
     worker_sync<WW>();
-    copy_out<WW>(c, na->hidden + (int64_t)l * c.a->R * E);
+    copy_out<WW>(c, na->hidden_out + (int64_t)l * c.a->R * E);
     if (want_value && hh == 0 && c.a->value) {
         int64_t gr;
         int env, i;
@@ -1216,7 +1217,8 @@ static int fill_net(pf::NetArgs &na, const marl_dhgn_weights *w, const marl_poli
     na.head_b = w->head_b;
     na.head_w_eff = is_actor ? nullptr : w->head_w;
     na.emb_out = io->d_emb_out;
-    na.hidden = io->d_hidden;
+    na.hidden_in = io->d_hidden;
+    na.hidden_out = io->d_hidden_out ? io->d_hidden_out : io->d_hidden;
     na.all_ones = is_actor ? 0 : 1;
     return MARL_OK;
 }

@@ -19,12 +19,13 @@ class DhgnWeights(C.Structure):
 
 
 class PolicyNetIO(C.Structure):
-    _fields_ = [("d_packed", C.c_void_p), ("d_hist", C.c_void_p * 3), ("d_emb_out", C.c_void_p), ("d_hidden", C.c_void_p)]
+    _fields_ = [("d_packed", C.c_void_p), ("d_hist", C.c_void_p * 3), ("d_emb_out", C.c_void_p), ("d_hidden", C.c_void_p),
+                ("d_hidden_out", C.c_void_p)]
 
 
 class PolicyStep(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "N", "O", "E", "depth", "action_dim", "t", "deterministic", "force_action",
-                                         "reserved")] + \
+                                         "variant")] + \
                [("seed", C.c_uint64)] + \
                [(n, C.c_void_p) for n in ("d_p_state", "d_e_state", "d_oxy", "d_map_id", "d_o_count", "d_p_adj_bits",
                                           "d_e_adj", "d_o_adj_bits", "d_action", "d_logp", "d_value", "d_debug")]
@@ -50,6 +51,7 @@ class FusedRolloutStep:
         self.depth, self.E, self.A = int(mappo.depth), 128, int(mappo.action_dim)
         dev = mappo.device
         self._keep = []
+        self._next_hidden = {}
         enc = mappo.actor.shared_net
         self.w = {}
         self.packed = {}
@@ -87,20 +89,23 @@ class FusedRolloutStep:
             keep.append(buf)
 
     def step(self, engine, oxy_i32, o_count, t, seed, deterministic, hist_a, hist_c, emb_a, emb_c, ha, hc, action, logp, value,
-             nets=("actor", "critic"), force_action=False, debug=None):
+             nets=("actor", "critic"), force_action=False, debug=None, variant=0):
         """hist_*: list (k = 0 newest) of [B,N,E] tensors or None (zeros); emb_*: [B,N,E] outputs; ha/hc: [2,B*N,E] in/out;
-        action i32 [B,N], logp / value f32 [B,N] outputs."""
+        action i32 [B,N], logp / value f32 [B,N] outputs.
+        The kernel reads the previous hidden state from one buffer and writes the new one to another; afterwards the two tensors
+        trade their storage, so for the caller `ha` / `hc` are updated "in place" (views taken before the call keep the old state)."""
         s = PolicyStep()
         s.B, s.N, s.O, s.E, s.depth, s.action_dim = engine.B, engine.N, engine.O, self.E, self.depth, self.A
         s.t, s.deterministic, s.seed = int(t), 1 if deterministic else 0, int(seed) & 0xFFFFFFFFFFFFFFFF
         s.force_action = 1 if force_action else 0
+        s.variant = int(variant)
         P = _lib.ptr
         s.d_debug = P(debug) if debug is not None else None
         s.d_p_state, s.d_e_state, s.d_oxy, s.d_map_id, s.d_o_count = (P(engine.p_state), P(engine.e_state), P(oxy_i32),
                                                                         P(engine.map_id), P(o_count))
         s.d_p_adj_bits, s.d_e_adj, s.d_o_adj_bits = P(engine.p_adj_bits), P(engine.e_adj), P(engine.o_adj_bits)
         s.d_action, s.d_logp, s.d_value = P(action), P(logp), P(value)
-        ios = {}
+        ios, swaps = {}, []
         for name, hist, emb, hid in (("actor", hist_a, emb_a, ha), ("critic", hist_c, emb_c, hc)):
             if name not in nets:
                 continue
@@ -108,9 +113,17 @@ class FusedRolloutStep:
             io.d_packed = self.packed[name].data_ptr()
             for k in range(self.depth):
                 io.d_hist[k] = P(hist[k]) if hist[k] is not None else None
-            io.d_emb_out, io.d_hidden = P(emb), P(hid)
+            nxt = self._next_hidden.get(name)
+            if nxt is None or nxt.shape != hid.shape or nxt.device != hid.device:
+                nxt = self._next_hidden[name] = torch.empty_like(hid)
+            assert hid.is_contiguous()
+            io.d_emb_out, io.d_hidden, io.d_hidden_out = P(emb), P(hid), P(nxt)
             ios[name] = io
+            swaps.append((hid, name))
         a_w, a_io = (C.byref(self.w["actor"]), C.byref(ios["actor"])) if "actor" in ios else (None, None)
         c_w, c_io = (C.byref(self.w["critic"]), C.byref(ios["critic"])) if "critic" in ios else (None, None)
         _lib.check(self.lib.marl_policy_rollout_step(C.byref(s), a_w, a_io, c_w, c_io, _lib.stream_ptr()),
                    "marl_policy_rollout_step")
+        for hid, name in swaps:                              # the caller's tensor now holds the new state, ours the old buffer
+            nxt = self._next_hidden[name]
+            hid.data, nxt.data = nxt.data, hid.data

@@ -392,12 +392,15 @@ typedef struct marl_policy_net_io {
     const void *d_packed;        /* marl_policy_pack output (1024-byte aligned, marl_policy_pack_bytes bytes) */
     const float *d_hist[3];      /* history embeddings [B,N,E], k = 0 the most recent; NULL = zeros (:750-752) */
     float *d_emb_out;            /* [B,N,E] this step's embedding (stored at t+D of the history buffer) */
-    float *d_hidden;             /* [2, B*N, E] GRU hidden state, updated in place */
+    float *d_hidden;             /* [2, B*N, E] GRU hidden state (input; also the output when d_hidden_out is NULL) */
+    float *d_hidden_out;         /* NULL (update d_hidden in place) or a distinct [2, B*N, E] buffer for the new state: the caller
+                                    ping-pongs the two.  Required by the two-CTA-per-SM kernel variant (its GRU runs in two
+                                    column halves and re-reads the previous state) */
 } marl_policy_net_io;
 typedef struct marl_policy_step {
     int32_t B, N, O, E, depth, action_dim, t, deterministic;
     int32_t force_action;        /* != 0: d_action is an INPUT (teacher forcing); d_logp is the log-prob of that action */
-    int32_t reserved;
+    int32_t variant;             /* 0 = choose; 1 = one CTA per SM (16 worker warps); 2 = two CTAs per SM (needs d_hidden_out) */
     uint64_t seed;               /* sampling: same counter RNG as marl_act_head (keyed by seed, row, t) */
     const double *d_p_state;     /* [B,N,4] */
     const double *d_e_state;     /* [B,4] */
