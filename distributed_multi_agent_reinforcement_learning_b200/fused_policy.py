@@ -92,8 +92,9 @@ class FusedRolloutStep:
              nets=("actor", "critic"), force_action=False, debug=None, variant=0):
         """hist_*: list (k = 0 newest) of [B,N,E] tensors or None (zeros); emb_*: [B,N,E] outputs; ha/hc: [2,B*N,E] in/out;
         action i32 [B,N], logp / value f32 [B,N] outputs.
-        The kernel reads the previous hidden state from one buffer and writes the new one to another; afterwards the two tensors
-        trade their storage, so for the caller `ha` / `hc` are updated "in place" (views taken before the call keep the old state)."""
+        variant: 0 / 1 = one CTA per SM (the default; hidden state updated in place), 2 = two CTAs per SM: that kernel reads the
+        previous hidden state from one buffer and writes the new one to another; afterwards the two tensors trade their storage, so
+        for the caller `ha` / `hc` are still updated "in place" (views taken before the call keep the old state)."""
         s = PolicyStep()
         s.B, s.N, s.O, s.E, s.depth, s.action_dim = engine.B, engine.N, engine.O, self.E, self.depth, self.A
         s.t, s.deterministic, s.seed = int(t), 1 if deterministic else 0, int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -113,13 +114,15 @@ class FusedRolloutStep:
             io.d_packed = self.packed[name].data_ptr()
             for k in range(self.depth):
                 io.d_hist[k] = P(hist[k]) if hist[k] is not None else None
-            nxt = self._next_hidden.get(name)
-            if nxt is None or nxt.shape != hid.shape or nxt.device != hid.device:
-                nxt = self._next_hidden[name] = torch.empty_like(hid)
             assert hid.is_contiguous()
-            io.d_emb_out, io.d_hidden, io.d_hidden_out = P(emb), P(hid), P(nxt)
+            io.d_emb_out, io.d_hidden, io.d_hidden_out = P(emb), P(hid), None
+            if int(variant) == 2:                            # the two-CTA-per-SM kernel re-reads the previous state: separate output
+                nxt = self._next_hidden.get(name)
+                if nxt is None or nxt.shape != hid.shape or nxt.device != hid.device:
+                    nxt = self._next_hidden[name] = torch.empty_like(hid)
+                io.d_hidden_out = P(nxt)
+                swaps.append((hid, name))
             ios[name] = io
-            swaps.append((hid, name))
         a_w, a_io = (C.byref(self.w["actor"]), C.byref(ios["actor"])) if "actor" in ios else (None, None)
         c_w, c_io = (C.byref(self.w["critic"]), C.byref(ios["critic"])) if "critic" in ios else (None, None)
         _lib.check(self.lib.marl_policy_rollout_step(C.byref(s), a_w, a_io, c_w, c_io, _lib.stream_ptr()),

@@ -33,8 +33,9 @@ def _words(packed_bytes, n_bits):
     return np.ascontiguousarray(b).view(np.uint32).astype(np.int64).astype(np.uint32).view(np.int32).reshape(*packed_bytes.shape[:-1], nw)
 
 
+@pytest.mark.parametrize("variant", [1, 2], ids=["one_cta_per_sm", "two_ctas_per_sm"])
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-4] for p in FIXTURES])
-def test_fused_step_reproduces_reference_rollout_buffer(path):
+def test_fused_step_reproduces_reference_rollout_buffer(path, variant):
     from distributed_multi_agent_reinforcement_learning_b200.fused_policy import FusedRolloutStep
     from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
     fx = np.load(path)
@@ -64,7 +65,7 @@ def test_fused_step_reproduces_reference_rollout_buffer(path):
             back, src = k // 2 + 1, (hist_c if k % 2 == 0 else hist_a)
             hist.append(src[:, t - back + depth].contiguous() if t - back >= 0 else None)
         action = cu(fx["a_n"][:, t].astype(np.int32))
-        fused.step(eng, oxy, o_count, t, 0, False, hist, hist, emb_a, emb_c, ha, hc, action, logp, value, force_action=True)
+        fused.step(eng, oxy, o_count, t, 0, False, hist, hist, emb_a, emb_c, ha, hc, action, logp, value, force_action=True, variant=variant)
         torch.cuda.synchronize()
         tol = dict(rtol=1e-5, atol=2e-5)
         torch.testing.assert_close(emb_a, hist_a[:, t + depth], **tol)
@@ -73,8 +74,9 @@ def test_fused_step_reproduces_reference_rollout_buffer(path):
         torch.testing.assert_close(logp, cu(fx["a_logprob_n"][:, t]), **tol)
 
 
+@pytest.mark.parametrize("variant", [1, 2], ids=["one_cta_per_sm", "two_ctas_per_sm"])
 @pytest.mark.parametrize("B,N,D,steps", [(300, 8, 1, 4), (70, 5, 3, 5), (9, 16, 2, 3), (7, 20, 1, 2), (45, 4, 1, 3)])
-def test_fused_step_matches_unfused_kernels(B, N, D, steps):
+def test_fused_step_matches_unfused_kernels(B, N, D, steps, variant):
     from distributed_multi_agent_reinforcement_learning_b200 import policy_ops as ops
     from distributed_multi_agent_reinforcement_learning_b200.fused_policy import FusedRolloutStep
     from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
@@ -123,7 +125,7 @@ def test_fused_step_matches_unfused_kernels(B, N, D, steps):
             emb_a, emb_c = torch.empty(B, N, E, device=dev), torch.empty(B, N, E, device=dev)
             act, logp, value = (torch.zeros(B, N, dtype=torch.int32, device=dev), torch.empty(B, N, device=dev),
                                 torch.empty(B, N, device=dev))
-            fused.step(env, oxy_i, o_count, t, 77, False, hist_in, hist_in, emb_a, emb_c, ha_f, hc_f, act, logp, value)
+            fused.step(env, oxy_i, o_count, t, 77, False, hist_in, hist_in, emb_a, emb_c, ha_f, hc_f, act, logp, value, variant=variant)
             torch.cuda.synchronize()
             torch.testing.assert_close(emb_a, ea, **tol)
             torch.testing.assert_close(emb_c, ec, **tol)
@@ -137,12 +139,12 @@ def test_fused_step_matches_unfused_kernels(B, N, D, steps):
             ha_g, hc_g = ha.clone(), hc.clone()
             forced = a_ref.view(B, N).clone()
             fused.step(env, oxy_i, o_count, t, 77, False, hist_in, hist_in, emb_a, emb_c, ha_g, hc_g, forced, logp, value,
-                       force_action=True)
+                       force_action=True, variant=variant)
             torch.testing.assert_close(logp.view(-1), lp_ref, **tol)
             # critic-only launch (bootstrap value)
             hc_h, val2 = hc.clone(), torch.empty(B, N, device=dev)
             fused.step(env, oxy_i, o_count, t, 77, False, hist_in, hist_in, emb_a, emb_c, ha_g, hc_h, None, None, val2,
-                       nets=("critic",))
+                       nets=("critic",), variant=variant)
             torch.testing.assert_close(val2, value, rtol=0, atol=0)
             ha, hc = ha_ref, hc_ref
             hist_in = [ec.view(B, N, E)] + hist_in[:-1] if D > 1 else [ec.view(B, N, E)]

@@ -38,7 +38,7 @@ for it in range(3):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     s.record()
-    fused.step(env, oxy_i, o_count, it, 1, False, hist, hist, emb_a, emb_c, ha, hc, act, logp, val, debug=dbg)
+    fused.step(env, oxy_i, o_count, it, 1, False, hist, hist, emb_a, emb_c, ha, hc, act, logp, val, debug=dbg, variant=int(os.environ.get("MARL_VARIANT", "0")))
     e.record()
     e.synchronize()
     print("launch ms", s.elapsed_time(e))
