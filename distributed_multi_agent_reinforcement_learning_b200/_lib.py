@@ -92,6 +92,9 @@ _PROTOTYPES = {
     "marl_gru_pack": (C.c_int, [_VP, _VP, _VP]),
     "marl_gru_seq_fwd": (C.c_int, [_I32, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "marl_gru_seq_bwd": (C.c_int, [_I32, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "marl_relu_bwd": (C.c_int, [_I64, _VP, _VP, _VP, _VP]),
+    "marl_skinny_wgrad_workspace_bytes": (_I64, [_I64, _I32, _I32]),
+    "marl_skinny_wgrad": (C.c_int, [_I64, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _I64, _VP, _VP, _VP]),
     "marl_wgrad_workspace_bytes": (_I64, [_I64, _I32, _I32]),
     "marl_wgrad_tf32x3": (C.c_int, [_I64, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _I64, _VP, _I32, _VP, _VP]),
     "marl_rowgemm_pack_bytes": (_I64, [_I32, _I32]),

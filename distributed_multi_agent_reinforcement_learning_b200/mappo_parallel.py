@@ -113,7 +113,7 @@ class DHGN(nn.Module):
         emb3 = ops.linear(agg.view(S * N * 3, E), av.weight, av.bias, relu=True).view(S * N, 3 * E)
         # semantic layer on [p | emb0 | emb1 | emb2] without materialising the concatenation: the 4-wide state part is
         # a rank-4 update handed to the GEMM as its additive input
-        p_term = torch.addmm(sem.bias, graph.p.view(S * N, 4), sem.weight[:, :4].t())
+        p_term = ops.skinny_linear(graph.p.view(S * N, 4), sem.weight[:, :4], sem.bias)
         h = ops.linear(emb3, sem.weight[:, 4:], None, add=p_term)
         for k in range(self.depth):
             hk = hist[k]

@@ -171,6 +171,47 @@ def wgrad(dy, x, out=None, col0=0, dbias=None):
     return out
 
 
+def relu_bwd(dy, out):
+    """dy * (out > 0) in one pass (backward of a ReLU fused into a GEMM epilogue)."""
+    if dy.numel() % 4 or not out.is_contiguous() or dy.data_ptr() % 16 or out.data_ptr() % 16:
+        return dy * (out > 0)
+    dst = torch.empty_like(dy)
+    _lib.check(_L().marl_relu_bwd(dy.numel(), dy.data_ptr(), out.data_ptr(), dst.data_ptr(), _lib.stream_ptr()), "marl_relu_bwd")
+    return dst
+
+
+class _SkinnyLinear(torch.autograd.Function):
+    """bias + p @ W4^T for a 4- or 8-wide input that needs no gradient (the pursuer-state part of the semantic layer,
+    DHGN/mappo_parallel.py:286,303).  Backward: weight and bias gradients in ONE pass over dY (marl_skinny_wgrad) instead of a
+    [K, R] x [R, E] library GEMM (a 1 ms SIMT sgemm at R = 492 K) plus a column-sum kernel."""
+
+    @staticmethod
+    def forward(ctx, p, W4, bias):
+        ctx.save_for_backward(p)
+        ctx.shape = (W4.shape[0], W4.shape[1])
+        return torch.addmm(bias, p, W4.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        (p,) = ctx.saved_tensors
+        N, K = ctx.shape
+        dy = dy.contiguous()
+        R = dy.shape[0]
+        dW = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+        db = torch.empty(N, dtype=torch.float32, device=dy.device)
+        ws = torch.empty(int(_L().marl_skinny_wgrad_workspace_bytes(R, N, K)), dtype=torch.uint8, device=dy.device)
+        _lib.check(_L().marl_skinny_wgrad(R, N, K, dy.data_ptr(), dy.stride(0), p.data_ptr(), p.stride(0), dW.data_ptr(), dW.stride(0),
+                                          db.data_ptr(), ws.data_ptr(), _lib.stream_ptr()), "marl_skinny_wgrad")
+        return None, dW, db
+
+
+def skinny_linear(p, W4, bias):
+    """bias + p @ W4^T, p [R, 4 or 8] (data, no gradient), W4 [E, K] (may be a column slice of a wider weight)."""
+    if p.is_cuda and p.dtype == torch.float32 and p.dim() == 2 and p.shape[1] in (4, 8) and p.stride(1) == 1 and not p.requires_grad:
+        return _SkinnyLinear.apply(p, W4, bias)
+    return torch.addmm(bias, p, W4.t())
+
+
 class _LinearTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, x2, W, bias, add, relu):
@@ -184,9 +225,9 @@ class _LinearTC(torch.autograd.Function):
     def backward(ctx, dy):
         x, x2, W, out = ctx.saved_tensors
         has_x2, has_bias, has_add = ctx.has
-        if ctx.relu:
-            dy = dy * (out > 0)
         dy = dy.contiguous()
+        if ctx.relu:
+            dy = relu_bwd(dy, out)
         K1 = x.shape[1]
         need = ctx.needs_input_grad
         dx = dx2 = dW = db = dadd = None

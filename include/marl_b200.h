@@ -467,6 +467,17 @@ int marl_rowgemm_tf32x3(int64_t M, int32_t N, int32_t K1, int32_t K2, const floa
                         const void *d_packed, const float *d_bias, const float *d_D, int64_t ldd, float *d_C, int64_t ldc, int32_t relu,
                         void *stream);
 
+/* Training-side helpers behind `ac_loss.backward()` (DHGN/mappo_parallel.py:708).
+ * marl_relu_bwd: d_dst = d_out > 0 ? d_dy : 0 over n floats (backward of a ReLU fused into a GEMM epilogue; n % 4 == 0, 16-byte aligned).
+ * marl_skinny_wgrad: weight (and bias) gradient of a layer whose input is K_in = 4 or 8 wide - the state part of the semantic layer
+ * (:286,303): dW[n][k] = sum_r dY[r][n] P[r][k] written with row stride lddw (e.g. straight into columns 0..3 of the [E, 3E+4]
+ * gradient), d_dbias[n] = sum_r dY[r][n] (may be NULL).  Deterministic (fixed row slices, ordered reduction).
+ * d_workspace: marl_skinny_wgrad_workspace_bytes(R, N_out, K_in) bytes. */
+int marl_relu_bwd(int64_t n, const float *d_dy, const float *d_out, float *d_dst, void *stream);
+int64_t marl_skinny_wgrad_workspace_bytes(int64_t R, int32_t N_out, int32_t K_in);
+int marl_skinny_wgrad(int64_t R, int32_t N_out, int32_t K_in, const float *d_dY, int64_t lddy, const float *d_P, int64_t ldp,
+                      float *d_dW, int64_t lddw, float *d_dbias, void *d_workspace, void *stream);
+
 /* torch.nn.utils.clip_grad_norm_ (:710-711) and torch.optim.Adam.step (runner.py:72-78) on flat fp32 arenas. */
 int64_t marl_clip_workspace_bytes(int64_t n);
 int marl_clip_grad_norm(int64_t n, float *d_grad, float max_norm, void *d_workspace, float *d_total_norm, void *stream);

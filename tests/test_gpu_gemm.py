@@ -153,3 +153,28 @@ def test_rowgemm_matches_fp64(M, N, K1, K2, relu, use_add):
     ref.backward(dout.double())
     for mine, theirs in ((gx, x.grad), (gW, W.grad), (gb, b.grad)) + (((gx2, x2.grad),) if x2 is not None else ()):
         assert (mine.double() - theirs.double()).abs().max().item() <= 5e-6 * theirs.abs().max().item() + 1e-7
+
+
+@pytest.mark.parametrize("R,N,K", [(1000, 128, 4), (70001, 128, 4), (333, 96, 8)])
+def test_skinny_wgrad_and_relu_bwd(R, N, K):
+    """Weight / bias gradient of a 4- or 8-wide input layer in one pass over dY, and the fused ReLU backward."""
+    from distributed_multi_agent_reinforcement_learning_b200 import policy_ops as ops
+    g = torch.Generator(device="cuda").manual_seed(R)
+    p = torch.randn(R, K, device="cuda", generator=g)
+    W = torch.randn(N, K + 3, device="cuda", generator=g).requires_grad_(True)
+    b = torch.randn(N, device="cuda", generator=g).requires_grad_(True)
+    dy = torch.randn(R, N, device="cuda", generator=g)
+    out = ops.skinny_linear(p, W[:, :K], b)
+    torch.testing.assert_close(out, torch.addmm(b, p, W[:, :K].t()), rtol=0, atol=0)
+    out.backward(dy)
+    ref_w, ref_b = dy.double().t() @ p.double(), dy.double().sum(0)
+    scale = float(ref_w.abs().max())
+    assert float((W.grad[:, :K].double() - ref_w).abs().max()) <= 2e-6 * max(1.0, scale) * (R ** 0.5) / 10
+    assert float((b.grad.double() - ref_b).abs().max()) <= 2e-6 * max(1.0, float(ref_b.abs().max())) * (R ** 0.5) / 10
+    assert not W.grad[:, K:].any()
+    g1, g2 = W.grad.clone(), None
+    W.grad = None
+    ops.skinny_linear(p, W[:, :K], b).backward(dy)
+    assert torch.equal(W.grad, g1)                                  # deterministic
+    y = torch.randn(R, N, device="cuda", generator=g)
+    torch.testing.assert_close(ops.relu_bwd(dy, y), dy * (y > 0), rtol=0, atol=0)
