@@ -719,42 +719,50 @@ relu_bwd_kernel(int64_t n4, const float4 *__restrict__ dy, const float4 *__restr
 // sum over the rows of slice s of dY[r][n] * P[r][k], k < K <= 8, plus k = K: sum of dY[r][n] (the bias gradient).
 // One thread per output feature n (coalesced rows of dY), the row of P is a broadcast load.  Deterministic: fixed slices,
 // reduced in order by skinny_wgrad_reduce_kernel.
-template <int K>
+template <int KMAX>
 __global__ void __launch_bounds__(128)
-skinny_wgrad_kernel(int64_t R, int N, const float *__restrict__ dY, int64_t lddy, const float *__restrict__ P, int64_t ldp,
+skinny_wgrad_kernel(int64_t R, int N, int K, const float *__restrict__ dY, int64_t lddy, const float *__restrict__ P, int64_t ldp,
                     int64_t rows_per_slice, float *__restrict__ partial)
 {
     const int n = blockIdx.y * 128 + threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_slice;
     int64_t r1 = r0 + rows_per_slice;
     if (r1 > R) r1 = R;
-    float acc[K + 1];
+    float acc[KMAX], sum = 0.f;
 #pragma unroll
-    for (int k = 0; k <= K; ++k) acc[k] = 0.f;
+    for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
     if (n < N) {
 #pragma unroll 4
         for (int64_t r = r0; r < r1; ++r) {
             const float g = dY[r * lddy + n];
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = fmaf(g, __ldg(P + r * ldp + k), acc[k]);
-            acc[K] += g;
+            for (int k = 0; k < KMAX; ++k)
+                if (k < K) acc[k] = fmaf(g, __ldg(P + r * ldp + k), acc[k]);
+            sum += g;
         }
         float *o = partial + ((size_t)blockIdx.x * N + n) * (K + 1);
 #pragma unroll
-        for (int k = 0; k <= K; ++k) o[k] = acc[k];
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) o[k] = acc[k];
+        o[K] = sum;
     }
 }
+// one warp per output (n, k <= K): lanes stride over the slices, then a fixed shuffle tree (deterministic)
 __global__ void __launch_bounds__(128)
 skinny_wgrad_reduce_kernel(int slices, int N, int K, const float *__restrict__ partial, float *__restrict__ dW, int64_t lddw,
                            float *__restrict__ dbias)
 {
-    const int idx = blockIdx.x * 128 + threadIdx.x;       // (n, k) with k <= K
+    const int idx = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;       // (n, k) with k <= K
     if (idx >= N * (K + 1)) return;
     const int n = idx / (K + 1), k = idx - n * (K + 1);
     float acc = 0.f;
-    for (int s = 0; s < slices; ++s) acc += partial[((size_t)s * N + n) * (K + 1) + k];
-    if (k < K) dW[(int64_t)n * lddw + k] = acc;
-    else if (dbias) dbias[n] = acc;
+    for (int s = lane; s < slices; s += 32) acc += partial[((size_t)s * N + n) * (K + 1) + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        if (k < K) dW[(int64_t)n * lddw + k] = acc;
+        else if (dbias) dbias[n] = acc;
+    }
 }
 
 }  // namespace marl
@@ -770,28 +778,35 @@ extern "C" int marl_relu_bwd(int64_t n, const float *d_dy, const float *d_out, f
     return check_launch("relu_bwd_kernel");
 }
 
+static int64_t skinny_slices(int64_t R)
+{
+    const int64_t cap = 148 * 16;                       // 16 four-warp CTAs per SM: the row loop is a latency chain, it needs the warps
+    const int64_t s = (R + 63) / 64;
+    return s < cap ? (s < 1 ? 1 : s) : cap;
+}
+
 extern "C" int64_t marl_skinny_wgrad_workspace_bytes(int64_t R, int32_t N_out, int32_t K_in)
 {
-    if (R <= 0 || N_out <= 0 || K_in <= 0 || K_in > 8) return -1;
-    const int64_t slices = R < 592 * 64 ? (R + 63) / 64 : 592;
-    return slices * N_out * (K_in + 1) * 4;
+    if (R <= 0 || N_out <= 0 || K_in <= 0 || K_in > 16) return -1;
+    return skinny_slices(R) * N_out * (K_in + 1) * 4;
 }
 
 extern "C" int marl_skinny_wgrad(int64_t R, int32_t N_out, int32_t K_in, const float *d_dY, int64_t lddy, const float *d_P, int64_t ldp,
                                  float *d_dW, int64_t lddw, float *d_dbias, void *d_workspace, void *stream)
 {
-    MARL_REQUIRE(R > 0 && N_out > 0 && (K_in == 4 || K_in == 8), "marl_skinny_wgrad: R=%lld N_out=%d K_in=%d (4 or 8)", (long long)R, N_out, K_in);
+    MARL_REQUIRE(R > 0 && N_out > 0 && K_in >= 1 && K_in <= 16, "marl_skinny_wgrad: R=%lld N_out=%d K_in=%d (1..16)", (long long)R, N_out, K_in);
     MARL_REQUIRE(d_dY && d_P && d_dW && d_workspace && lddy >= N_out && ldp >= K_in && lddw >= K_in, "marl_skinny_wgrad: bad pointer / leading dimension");
-    const int64_t slices = R < 592 * 64 ? (R + 63) / 64 : 592;
+    const int64_t slices = skinny_slices(R);
     const int64_t rps = (R + slices - 1) / slices;
     float *partial = static_cast<float *>(d_workspace);
     const dim3 grid((unsigned)slices, (unsigned)((N_out + 127) / 128));
-    if (K_in == 4) skinny_wgrad_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(R, N_out, d_dY, lddy, d_P, ldp, rps, partial);
-    else skinny_wgrad_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>(R, N_out, d_dY, lddy, d_P, ldp, rps, partial);
+    if (K_in <= 4) skinny_wgrad_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(R, N_out, K_in, d_dY, lddy, d_P, ldp, rps, partial);
+    else if (K_in <= 8) skinny_wgrad_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>(R, N_out, K_in, d_dY, lddy, d_P, ldp, rps, partial);
+    else skinny_wgrad_kernel<16><<<grid, 128, 0, (cudaStream_t)stream>>>(R, N_out, K_in, d_dY, lddy, d_P, ldp, rps, partial);
     int rc = check_launch("skinny_wgrad_kernel");
     if (rc) return rc;
     const int total = N_out * (K_in + 1);
-    skinny_wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>((int)slices, N_out, K_in, partial, d_dW, lddw, d_dbias);
+    skinny_wgrad_reduce_kernel<<<(total + 3) / 4, 128, 0, (cudaStream_t)stream>>>((int)slices, N_out, K_in, partial, d_dW, lddw, d_dbias);
     return check_launch("skinny_wgrad_reduce_kernel");
 }
 

@@ -205,6 +205,19 @@ class _SkinnyLinear(torch.autograd.Function):
         return None, dW, db
 
 
+def skinny_outer(y, p):
+    """y^T @ p for y [R, N], p [R, K <= 16] (row-major): [N, K], deterministic, one pass over y."""
+    R, N = y.shape
+    K = p.shape[1]
+    if not (y.is_cuda and y.dtype == torch.float32 and p.dtype == torch.float32 and K <= 16 and y.stride(1) == 1 and p.stride(1) == 1):
+        return y.t() @ p
+    out = torch.empty(N, K, dtype=torch.float32, device=y.device)
+    ws = torch.empty(int(_L().marl_skinny_wgrad_workspace_bytes(R, N, K)), dtype=torch.uint8, device=y.device)
+    _lib.check(_L().marl_skinny_wgrad(R, N, K, y.data_ptr(), y.stride(0), p.data_ptr(), p.stride(0), out.data_ptr(), out.stride(0),
+                                      None, ws.data_ptr(), _lib.stream_ptr()), "marl_skinny_wgrad")
+    return out
+
+
 def skinny_linear(p, W4, bias):
     """bias + p @ W4^T, p [R, 4 or 8] (data, no gradient), W4 [E, K] (may be a column slice of a wider weight)."""
     if p.is_cuda and p.dtype == torch.float32 and p.dim() == 2 and p.shape[1] in (4, 8) and p.stride(1) == 1 and not p.requires_grad:
@@ -452,7 +465,7 @@ class _PPOHead(torch.autograd.Function):
         dl = dlogits * (g_actor / sums[2])
         dv = dvalue * (g_critic / sums[2])
         d_feat_a = torch.mm(dl, Wa)
-        dWa = torch.mm(dl.t(), feat_a)
+        dWa = skinny_outer(feat_a, dl).t()               # [A, E] = dl^T feat_a in one pass over feat_a (a 1 ms SIMT sgemm otherwise)
         dba = dl.sum(0)
         d_feat_c = dv.unsqueeze(1) * w_eff.unsqueeze(0)
         dw_eff = torch.mv(feat_c.t(), dv)

@@ -469,8 +469,8 @@ int marl_rowgemm_tf32x3(int64_t M, int32_t N, int32_t K1, int32_t K2, const floa
 
 /* Training-side helpers behind `ac_loss.backward()` (DHGN/mappo_parallel.py:708).
  * marl_relu_bwd: d_dst = d_out > 0 ? d_dy : 0 over n floats (backward of a ReLU fused into a GEMM epilogue; n % 4 == 0, 16-byte aligned).
- * marl_skinny_wgrad: weight (and bias) gradient of a layer whose input is K_in = 4 or 8 wide - the state part of the semantic layer
- * (:286,303): dW[n][k] = sum_r dY[r][n] P[r][k] written with row stride lddw (e.g. straight into columns 0..3 of the [E, 3E+4]
+ * marl_skinny_wgrad: weight (and bias) gradient of a layer whose input is K_in <= 16 wide - the state part of the semantic layer
+ * (:286,303), or, with the roles of the operands swapped, the 9-row actor head (:437): dW[n][k] = sum_r dY[r][n] P[r][k] written with row stride lddw (e.g. straight into columns 0..3 of the [E, 3E+4]
  * gradient), d_dbias[n] = sum_r dY[r][n] (may be NULL).  Deterministic (fixed row slices, ordered reduction).
  * d_workspace: marl_skinny_wgrad_workspace_bytes(R, N_out, K_in) bytes. */
 int marl_relu_bwd(int64_t n, const float *d_dy, const float *d_out, float *d_dst, void *stream);

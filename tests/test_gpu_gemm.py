@@ -178,3 +178,6 @@ def test_skinny_wgrad_and_relu_bwd(R, N, K):
     assert torch.equal(W.grad, g1)                                  # deterministic
     y = torch.randn(R, N, device="cuda", generator=g)
     torch.testing.assert_close(ops.relu_bwd(dy, y), dy * (y > 0), rtol=0, atol=0)
+    q = torch.randn(R, 9, device="cuda", generator=g)                # the actor head's shape: [E, 9] = feat^T dlogits
+    got, ref = ops.skinny_outer(dy, q), dy.double().t() @ q.double()
+    assert float((got.double() - ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max())) * (R ** 0.5) / 10
