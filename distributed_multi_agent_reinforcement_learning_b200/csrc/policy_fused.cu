@@ -112,6 +112,7 @@ struct StepArgs {
     float *logp, *value;
     uint64_t seed;
     int t, deterministic, force_action, net_first, net_count;
+    int64_t row_offset;   // RNG key offset of row 0 (sub-batch launches)
     long long *dbg;   // optional [grid,16] per-CTA phase cycle counters (profiling aid)
     NetArgs net[2];   // 0 actor, 1 critic
 };
@@ -1010,7 +1011,7 @@ __device__ void epi_head(const Ctx &c)
 #pragma unroll
         for (int k = 0; k < A; ++k) if (sm[k] > best) { best = sm[k]; act = k; }
     } else {
-        const uint64_t hsh = splitmix64(c.a->seed ^ splitmix64((uint64_t)gr * 0x100000001B3ull + (uint64_t)c.a->t));
+        const uint64_t hsh = splitmix64(c.a->seed ^ splitmix64((uint64_t)(gr + c.a->row_offset) * 0x100000001B3ull + (uint64_t)c.a->t));
         const float u = (float)(hsh >> 40) * (1.0f / 16777216.0f) * psum;
         float cs = 0.f;
         act = A - 1;
@@ -1473,6 +1474,7 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
     a.p_state = s->d_p_state; a.e_state = s->d_e_state; a.oxy = s->d_oxy; a.map_id = s->d_map_id; a.o_count = s->d_o_count;
     a.p_adj = s->d_p_adj_bits; a.e_adj = s->d_e_adj; a.o_adj = s->d_o_adj_bits;
     a.action = s->d_action; a.logp = s->d_logp; a.value = s->d_value; a.seed = s->seed; a.t = s->t; a.deterministic = s->deterministic; a.force_action = s->force_action;
+    a.row_offset = s->row_offset;
     a.dbg = static_cast<long long *>(s->d_debug);
     int rc;
     if (has_a) { rc = fill_net(a.net[0], actor_w, actor_io, s->depth, 1, s->action_dim, dual); if (rc) return rc; }

@@ -18,6 +18,8 @@ Reference quirks kept on purpose (parity is defined per phase):
   * gradients accumulate over minibatches and clip_grad_norm_ acts on the running accumulation (:708-711);
   * minibatches are sequential, unshuffled index ranges (:665).
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -533,7 +535,8 @@ class MAPPO:
 
     # ------------------------------------------------------------------------------------------------ rollout
     @torch.no_grad()
-    def rollout_batched(self, engine, arena, T=None, seed=0, deterministic=False, groups=1, use_fused=None, timers=None):
+    def rollout_batched(self, engine, arena, T=None, seed=0, deterministic=False, groups=1, use_fused=None, timers=None,
+                        pipelines=None):
         """MAPPO.run_episode (:742-827) for all B envs of a BatchedPursuitEnv at once, entirely on the GPU.
         Per step: observe kernel -> fused encoder (actor, then critic with all-ones adjacency) -> GRU cell -> heads ->
         closed-loop env kernel (evader move + pursuer step + reward-norm + store).  Fills `arena` plus the history /
@@ -589,9 +592,20 @@ class MAPPO:
                 b_.record()
                 timers.setdefault(name, []).append((a_, b_))
 
-            # The A* replanning due every `difficulty` steps only needs the env state, not the action: it runs on a side
-            # stream concurrently with the policy kernel (its long tail of slow searches then costs no wall time) and is
-            # joined before the env kernel consumes the paths.
+            # Env-group pipelines: the envs are independent, so the batch is cut into G contiguous groups, each stepping through
+            # the episode on its own stream (observe -> policy step || A* replan -> env step).  One group's small kernels and the
+            # long tail of its replanning (the slowest of its searches gates its env step) then overlap with the other groups'
+            # policy kernels instead of idling the GPU.  Same results for any G (the sampling RNG is keyed by the global row).
+            if pipelines is None:
+                pipelines = max(1, min(8, (B * N) // 8192)) if (timers is None and groups == 1) else 1
+                if os.environ.get("MARL_PIPELINES") and timers is None and groups == 1:      # tuning knob for tools/
+                    pipelines = int(os.environ["MARL_PIPELINES"])
+            if pipelines > 1 and timers is None and groups == 1:
+                self._rollout_pipelined(engine, arena, T, seed, deterministic, int(pipelines), fused, oxy_i, o_count, hist_a, hist_c,
+                                        act, logp, v, zeros_hist)
+                return self._train_batch(engine, arena, T, oxy, hist_a, hist_c, v, logp)
+            # Single pipeline.  The A* replanning due every `difficulty` steps only needs the env state, not the action: it runs
+            # on a side stream concurrently with the policy kernel and is joined before the env kernel consumes the paths.
             overlap = timers is None and groups == 1
             main = torch.cuda.current_stream()
             if overlap:
@@ -645,6 +659,71 @@ class MAPPO:
         w, _ = self.critic.head_weight()
         v[T] = torch.nn.functional.linear(feat_c[0], w, self.critic.Mean.bias).view(B, N)
         return self._train_batch(engine, arena, T, oxy, hist_a, hist_c, v, logp)
+
+    def _rollout_pipelined(self, engine, arena, T, seed, deterministic, G, fused, oxy_i, o_count, hist_a, hist_c, act, logp, v,
+                           zeros_hist):
+        """G independent env-group pipelines, one stream (+ one A* side stream) each; see rollout_batched."""
+        B, N, E, D, L = engine.B, engine.N, self.embedding_dim, self.depth, self.num_layers
+        dev = self.device
+        main = torch.cuda.current_stream()
+        if len(getattr(engine, "_pipe_streams", [])) < 2 * G:
+            engine._pipe_streams = [torch.cuda.Stream(device=dev) for _ in range(2 * G)]
+        rec_ptrs = arena.record_pointers()
+        diff = int(engine.params.difficulty)
+        fork = torch.cuda.Event()
+        fork.record(main)
+
+        class _View:                                     # what FusedRolloutStep.step reads from an engine, for envs [lo, hi)
+            pass
+
+        for g in range(G):
+            lo, hi = g * B // G, (g + 1) * B // G
+            st, side = engine._pipe_streams[2 * g], engine._pipe_streams[2 * g + 1]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                view = _View()
+                view.B, view.N, view.O = hi - lo, N, engine.O
+                ha = torch.zeros(L, (hi - lo) * N, E, dtype=torch.float32, device=dev)
+                hc = torch.zeros(L, (hi - lo) * N, E, dtype=torch.float32, device=dev)
+                sl = slice(lo, hi)
+
+                def hist_of(t):
+                    out = []
+                    for k in range(D):
+                        back = k // 2 + 1
+                        src = hist_c if k % 2 == 0 else hist_a
+                        out.append(src[t - back + D][sl] if t - back >= 0 else None)
+                    return out
+
+                def refresh():
+                    view.p_state, view.e_state, view.map_id = engine.p_state[sl], engine.e_state[sl], engine.map_id[sl]
+                    view.p_adj_bits, view.e_adj, view.o_adj_bits = engine.p_adj_bits[sl], engine.e_adj[sl], engine.o_adj_bits[sl]
+
+                refresh()
+                for t in range(T):
+                    join = None
+                    if t % diff == 0:
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                        side.wait_event(ev)
+                        engine.evader_replan(lo, hi, side)
+                        join = torch.cuda.Event()
+                        join.record(side)
+                    engine.observe(lo=lo, hi=hi)
+                    h_t = hist_of(t)
+                    fused.step(view, oxy_i, o_count, t, seed, deterministic, h_t, h_t, hist_a[t + D][sl], hist_c[t + D][sl], ha, hc,
+                               act[t][sl], logp[t][sl], v[t][sl], row_offset=lo * N)
+                    if join is not None:
+                        st.wait_event(join)
+                    engine._closed_chunk(arena, rec_ptrs, lo, hi, t, 1, act[t:t + 1], 0, seed, st)
+                engine.observe(lo=lo, hi=hi)
+                h_fin = [hist_c[T - 1 + D][sl]] + hist_of(T - 1)[:D - 1]
+                scratch = torch.empty(hi - lo, N, E, dtype=torch.float32, device=dev)
+                fused.step(view, oxy_i, o_count, T, seed, deterministic, h_fin, h_fin, scratch, scratch, ha, hc, None, None, v[T][sl],
+                           nets=("critic",), row_offset=lo * N)
+                done = torch.cuda.Event()
+                done.record(st)
+            main.wait_event(done)
 
     def _train_batch(self, engine, arena, T, oxy, hist_a, hist_c, v, logp):
         B, D, dev = engine.B, self.depth, self.device

@@ -196,13 +196,17 @@ class BatchedPursuitEnv:
                            torch.zeros(B, N, O, dtype=torch.float32, device=dev))
         return self._dense
 
-    def observe(self, dense=False):
-        """communicate() + sensor() for all envs.  Packed words always; dense fp32 (reference layout) on request."""
+    def observe(self, dense=False, lo=0, hi=None):
+        """communicate() + sensor() for all envs (or envs [lo, hi)).  Packed words always; dense fp32 (reference layout) on
+        request (whole batch only)."""
         d = self.dense_views() if dense else (None, None, None)
+        hi = self.B if hi is None else hi
+        sl = slice(lo, hi)
+        assert not dense or (lo == 0 and hi == self.B)
         _lib.check(self.lib.marl_env_observe(
-            self._pp(), self.B, self.M, _lib.ptr(self.p_state), _lib.ptr(self.e_state), _lib.ptr(self.grid_bits),
-            _lib.ptr(self.raser_bits), _lib.ptr(self.map_id), _lib.ptr(self.p_adj_bits), _lib.ptr(self.e_adj),
-            _lib.ptr(self.o_adj_bits), _lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.stream_ptr()),
+            self._pp(), hi - lo, self.M, _lib.ptr(self.p_state[sl]), _lib.ptr(self.e_state[sl]), _lib.ptr(self.grid_bits),
+            _lib.ptr(self.raser_bits), _lib.ptr(self.map_id[sl]), _lib.ptr(self.p_adj_bits[sl]), _lib.ptr(self.e_adj[sl]),
+            _lib.ptr(self.o_adj_bits[sl]), _lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.stream_ptr()),
             "marl_env_observe")
         self.launches += 1
         return d if dense else (self.p_adj_bits, self.e_adj, self.o_adj_bits)

@@ -412,6 +412,8 @@ typedef struct marl_policy_step {
     float *d_logp;               /* [B,N] out (actor) */
     float *d_value;              /* [B,N] out (critic) */
     void *d_debug;               /* NULL, or i64 [grid,16] per-CTA phase cycle counters (profiling aid) */
+    int64_t row_offset;          /* added to the row index in the sampling RNG key: a launch over envs [lo, hi) of a larger batch passes
+                                    lo * N and draws the same actions as the whole-batch launch */
 } marl_policy_step;
 /* Pre-splits (two-term fp16: hi = fp16(w), lo = fp16(w - hi)) and pre-swizzles every dense layer of one network into the shared-memory image the fused kernel
  * streams; call once per weight update. */
