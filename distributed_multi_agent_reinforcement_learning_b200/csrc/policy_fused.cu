@@ -26,6 +26,7 @@
 // Shared memory: X 64 KB (2 k-blocks of K = 64 x (hi 16 KB + lo 16 KB)) + 4 x 32 KB weight stages.
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace marl {
 namespace pf {
@@ -1347,11 +1348,14 @@ static int build_units(const marl_dhgn_weights *w, int depth, int is_actor, int 
     return n;
 }
 
-// Rows per work item: whole envs, at most 128 rows (one MMA M tile).  One CTA is resident per SM, so the launch runs in
+// Rows per work item: whole envs, at most 128 rows (one MMA M tile).  A caller that runs several launches concurrently (env-group
+// pipelines) asks for full tiles: 148 items on 148 SMs leave no SM for the neighbours' kernels and every collision costs a whole
+// extra wave (measured: 4 pipelines of 148 items 61.5 ms per episode, of 128 items 52.1 ms).  For a lone launch:
+// one CTA is resident per SM, so the launch runs in
 // ceil(items / SMs) waves; a slightly smaller tile that fills the last wave beats a full tile that leaves most SMs idle in it
 // (32768 rows x 2 networks: 512 items of 128 rows = 3.46 -> 4 waves, 586 items of 112 rows = 3.96 waves).  Cost model of one item:
 // SIMT phases proportional to the rows, MMA phases constant (M = 128 regardless) - measured ~3 : 1 at 128 rows.
-static int choose_rows_per_tile(int64_t R, int N, int nets, int ctas_per_sm)
+static int choose_rows_per_tile(int64_t R, int N, int nets, int ctas_per_sm, int requested)
 {
     static int sms = 0;
     if (sms == 0) {
@@ -1359,6 +1363,11 @@ static int choose_rows_per_tile(int64_t R, int N, int nets, int ctas_per_sm)
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
     const int full = (ROWS / N) * N;
+    if (requested > 0 && requested <= full && requested % N == 0) return requested;
+    if (const char *force = getenv("MARL_POLICY_ROWS_PER_TILE")) {            // tuning knob for tools/: a multiple of N in [N, full]
+        const int v = atoi(force);
+        if (v >= N && v <= full && v % N == 0) return v;
+    }
     int best = full;
     double best_cost = 0.0;
     for (int rpt = full; rpt >= N && rpt * 4 >= full * 3; rpt -= N) {
@@ -1474,7 +1483,7 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
     MARL_REQUIRE(s->variant >= 0 && s->variant <= 2, "marl_policy_rollout_step: variant=%d (0..2)", s->variant);
     MARL_REQUIRE(s->variant != 2 || pingpong, "marl_policy_rollout_step: variant 2 needs d_hidden_out != d_hidden");
     const bool dual = s->variant == 2 || (s->variant == 0 && pingpong && pf::kDualByDefault && s->O <= pf::Mem<true>::OXY);
-    a.rows_per_tile = pf::choose_rows_per_tile(a.R, s->N, nets, dual ? 2 : 1);
+    a.rows_per_tile = pf::choose_rows_per_tile(a.R, s->N, nets, dual ? 2 : 1, s->tile_rows);
     a.n_tiles = (int)((a.R + a.rows_per_tile - 1) / a.rows_per_tile);
     a.p_state = s->d_p_state; a.e_state = s->d_e_state; a.oxy = s->d_oxy; a.map_id = s->d_map_id; a.o_count = s->d_o_count;
     a.p_adj = s->d_p_adj_bits; a.e_adj = s->d_e_adj; a.o_adj = s->d_o_adj_bits;

@@ -29,7 +29,7 @@ class PolicyStep(C.Structure):
                [("seed", C.c_uint64)] + \
                [(n, C.c_void_p) for n in ("d_p_state", "d_e_state", "d_oxy", "d_map_id", "d_o_count", "d_p_adj_bits",
                                           "d_e_adj", "d_o_adj_bits", "d_action", "d_logp", "d_value", "d_debug")] + \
-               [("row_offset", C.c_int64)]
+               [("row_offset", C.c_int64), ("tile_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 def supported(mappo):
@@ -90,7 +90,7 @@ class FusedRolloutStep:
             keep.append(buf)
 
     def step(self, engine, oxy_i32, o_count, t, seed, deterministic, hist_a, hist_c, emb_a, emb_c, ha, hc, action, logp, value,
-             nets=("actor", "critic"), force_action=False, debug=None, variant=0, row_offset=0):
+             nets=("actor", "critic"), force_action=False, debug=None, variant=0, row_offset=0, tile_rows=0):
         """hist_*: list (k = 0 newest) of [B,N,E] tensors or None (zeros); emb_*: [B,N,E] outputs; ha/hc: [2,B*N,E] in/out;
         action i32 [B,N], logp / value f32 [B,N] outputs.
         variant: 0 / 1 = one CTA per SM (the default; hidden state updated in place), 2 = two CTAs per SM: that kernel reads the
@@ -102,6 +102,7 @@ class FusedRolloutStep:
         s.force_action = 1 if force_action else 0
         s.variant = int(variant)
         s.row_offset = int(row_offset)
+        s.tile_rows = int(tile_rows)
         P = _lib.ptr
         s.d_debug = P(debug) if debug is not None else None
         s.d_p_state, s.d_e_state, s.d_oxy, s.d_map_id, s.d_o_count = (P(engine.p_state), P(engine.e_state), P(oxy_i32),

@@ -670,6 +670,7 @@ class MAPPO:
             engine._pipe_streams = [torch.cuda.Stream(device=dev) for _ in range(2 * G)]
         rec_ptrs = arena.record_pointers()
         diff = int(engine.params.difficulty)
+        full_tile = (128 // N) * N if N <= 128 else 0      # concurrent launches: full tiles, SMs left over for the neighbours
         fork = torch.cuda.Event()
         fork.record(main)
 
@@ -712,7 +713,7 @@ class MAPPO:
                     engine.observe(lo=lo, hi=hi)
                     h_t = hist_of(t)
                     fused.step(view, oxy_i, o_count, t, seed, deterministic, h_t, h_t, hist_a[t + D][sl], hist_c[t + D][sl], ha, hc,
-                               act[t][sl], logp[t][sl], v[t][sl], row_offset=lo * N)
+                               act[t][sl], logp[t][sl], v[t][sl], row_offset=lo * N, tile_rows=full_tile)
                     if join is not None:
                         st.wait_event(join)
                     engine._closed_chunk(arena, rec_ptrs, lo, hi, t, 1, act[t:t + 1], 0, seed, st)
@@ -720,7 +721,7 @@ class MAPPO:
                 h_fin = [hist_c[T - 1 + D][sl]] + hist_of(T - 1)[:D - 1]
                 scratch = torch.empty(hi - lo, N, E, dtype=torch.float32, device=dev)
                 fused.step(view, oxy_i, o_count, T, seed, deterministic, h_fin, h_fin, scratch, scratch, ha, hc, None, None, v[T][sl],
-                           nets=("critic",), row_offset=lo * N)
+                           nets=("critic",), row_offset=lo * N, tile_rows=full_tile)
                 done = torch.cuda.Event()
                 done.record(st)
             main.wait_event(done)

@@ -414,6 +414,10 @@ typedef struct marl_policy_step {
     void *d_debug;               /* NULL, or i64 [grid,16] per-CTA phase cycle counters (profiling aid) */
     int64_t row_offset;          /* added to the row index in the sampling RNG key: a launch over envs [lo, hi) of a larger batch passes
                                     lo * N and draws the same actions as the whole-batch launch */
+    int32_t tile_rows;           /* 0 = choose the rows per work item with the wave model (a lone launch: fill the last wave); > 0 = that
+                                    many rows (a multiple of N, <= 128) - launches that run concurrently with others (env-group
+                                    pipelines) use full tiles and leave SMs free for their neighbours */
+    int32_t reserved;
 } marl_policy_step;
 /* Pre-splits (two-term fp16: hi = fp16(w), lo = fp16(w - hi)) and pre-swizzles every dense layer of one network into the shared-memory image the fused kernel
  * streams; call once per weight update. */
