@@ -494,7 +494,9 @@ def run_ours(args):
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16 = the kind::f16 rate; the split issues 3 MMAs "
                                "per algorithmic product, so this kernel's ceiling is frac = 1/3)",
                 "algorithmic_flops_per_launch": flops_launch, "flops_per_agent_per_network": policy_flops_per_agent(N, env.O, cfg.algo.depth),
-                "avg_launch_us": pk["avg_us"], "share_of_step": pk["total_ms"] / ms_episode,
+                "avg_launch_us": pk["avg_us"], "share_of_step": pk["total_ms"] / sum(v["total_ms"] for v in kernel_table.values()),
+                "share_note": "share of the kernel time of one eager, single-pipeline episode (kernel_ms_per_episode); the timed episode is "
+                              "one CUDA graph of 4 env-group pipelines whose kernels overlap, so its wall time is below that sum",
                 "hbm_bytes_per_launch_algorithmic": bytes_launch,
                 "hbm_GBps_at_this_duration": bytes_launch / (pk["avg_us"] * 1e-6) / 1e9, "hbm_peak_GBps": hbm_peak,
                 "note": "SURVEY 8(d) FLOP count per agent and network (obstacle messages counted for all O slots: upper bound) x "
