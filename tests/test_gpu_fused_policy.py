@@ -185,14 +185,15 @@ def test_rollout_batched_fused_equals_unfused_rollout():
     assert np.isfinite(objC) and np.isfinite(objA)
 
 
-def test_rollout_pipelines_give_identical_episodes():
+@pytest.mark.parametrize("N,D", [(8, 1), (5, 2)])
+def test_rollout_pipelines_give_identical_episodes(N, D):
     """Env-group pipelines (independent sub-batches on their own streams) must not change anything: actions, rewards, states,
     embeddings, values, log-probs and Welford state are bit-identical for 1, 3 and 4 pipelines (the sampling RNG is keyed by the
     global row; rows do not interact across envs)."""
     from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
     from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv, RolloutArena
     import bench
-    B, N, M, T, D = 50, 8, 5, 23, 1
+    B, M, T = 50, 5, 23
     cfg = _cfg(D, N, T)
     torch.manual_seed(2)
     m = MAPPO(cfg, B, 5, "Learner")
