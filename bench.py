@@ -38,7 +38,8 @@ def workload_config(n_gpus):
     return {"workload": "pursuit_evasion_obstacles_8p_gru_c2", "num_pursuers": N_AGENTS, "envs_per_gpu": B_PER_GPU,
             "global_envs": B_PER_GPU * n_gpus, "max_steps": T_STEPS, "map": "60x55", "num_max_obstacle": 176,
             "map_pool_per_gpu": N_MAPS, "evader": "gpu A* (replan every 10 steps)",
-            "policy": "DHGN actor + critic (embedding 128, depth 1, 2-layer GRU) in the loop, random-init weights, fp32",
+            "policy": "DHGN actor + critic (embedding 128, depth 1, 2-layer GRU) in the loop, random-init weights, fp32-level arithmetic "
+                      "(fp32 SIMT + tensor-core GEMMs on two-term fp16 / 3xTF32 operand splits with fp32 accumulation)",
             "parallelism": f"dp{n_gpus} (independent env shards, no data-path collective)",
             "l2": "flushed between timed iterations (256 MiB write)"}
 
