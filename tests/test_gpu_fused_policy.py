@@ -216,3 +216,53 @@ def test_rollout_pipelines_give_identical_episodes(N, D):
     for other in out[1:]:
         for a, b in zip(out[0], other):
             assert torch.equal(a, b)
+
+
+def test_fused_step_full_size_env_permutation_equivariance():
+    """BASELINE config 2 size (4096 envs x 8 pursuers): envs are independent, so permuting the envs of the batch must permute every
+    output of the fused step bit for bit (embeddings, hidden states, values, arg-max actions, log-probs) - whatever tile, CTA or
+    warp an env lands in.  Also checks that the outputs are finite and that the critic does not depend on the adjacency."""
+    from distributed_multi_agent_reinforcement_learning_b200.fused_policy import FusedRolloutStep
+    from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
+    from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv
+    B, N, D, E = 4096, 8, 1, 128
+    cfg = _cfg(D, N, 150)
+    torch.manual_seed(11)
+    m = MAPPO(cfg, B, B // 10, "Learner")
+    with torch.no_grad():
+        for p in m.ac_parameters:
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+    env = BatchedPursuitEnv(cfg, B, num_maps=64)
+    env.reset_device(seed=21)
+    dev = env.device
+    w_eff, _ = m.critic.head_weight()
+    fused = FusedRolloutStep(m, w_eff)
+    oxy_i = env.boundary_xy.contiguous()
+    o_count = torch.clamp(env.boundary_count, max=env.O).contiguous()
+    g = torch.Generator(device=dev).manual_seed(4)
+    ha0 = 0.1 * torch.randn(2, B, N, E, device=dev, generator=g)
+    hc0 = 0.1 * torch.randn(2, B, N, E, device=dev, generator=g)
+    hist0 = 0.3 * torch.randn(B, N, E, device=dev, generator=g)
+    perm = torch.randperm(B, device=dev, generator=g)
+
+    def run(order):
+        e = BatchedPursuitEnv(cfg, B, num_maps=64)
+        for name in ("grid_bits", "inflated_bits", "boundary_bits", "boundary_count", "boundary_xy", "raser_bits"):
+            getattr(e, name).copy_(getattr(env, name))
+        e.p_state.copy_(env.p_state[order]); e.e_state.copy_(env.e_state[order]); e.map_id.copy_(env.map_id[order])
+        e.observe()
+        ha, hc = ha0[:, order].reshape(2, B * N, E).contiguous(), hc0[:, order].reshape(2, B * N, E).contiguous()
+        hist = [hist0[order].contiguous()]
+        emb_a, emb_c = torch.empty(B, N, E, device=dev), torch.empty(B, N, E, device=dev)
+        act, logp, val = torch.zeros(B, N, dtype=torch.int32, device=dev), torch.empty(B, N, device=dev), torch.empty(B, N, device=dev)
+        fused.step(e, oxy_i, o_count, 3, 1, True, hist, hist, emb_a, emb_c, ha, hc, act, logp, val)
+        torch.cuda.synchronize()
+        return emb_a, emb_c, ha.view(2, B, N, E), hc.view(2, B, N, E), act, logp, val
+
+    ident = torch.arange(B, device=dev)
+    a, b = run(ident), run(perm)
+    for x, y, batch_dim in zip(a, b, (0, 0, 1, 1, 0, 0, 0)):
+        assert torch.isfinite(x.float()).all()
+        assert torch.equal(x.index_select(batch_dim, perm), y)
+    assert len(torch.unique(a[4])) > 1                      # the arg-max policy is not degenerate on this batch
