@@ -677,18 +677,10 @@ class MAPPO:
         class _View:                                     # what FusedRolloutStep.step reads from an engine, for envs [lo, hi)
             pass
 
-        # Stagger: group g starts once group g-1 has finished `lag` steps.  All groups replan at the same step indices; started
-        # together they reach those steps at the same wall time, their A* launches pile up behind each other's policy kernels and
-        # every group then waits.  A few steps of offset put one group's replanning under the other groups' policy work.
-        lag = int(os.environ.get("MARL_PIPELINE_LAG", "0"))
-        gate = None
         for g in range(G):
             lo, hi = g * B // G, (g + 1) * B // G
             st, side = engine._pipe_streams[2 * g], engine._pipe_streams[2 * g + 1]
             st.wait_event(fork)
-            if gate is not None:
-                st.wait_event(gate)
-            gate = None
             with torch.cuda.stream(st):
                 view = _View()
                 view.B, view.N, view.O = hi - lo, N, engine.O
@@ -725,9 +717,6 @@ class MAPPO:
                     if join is not None:
                         st.wait_event(join)
                     engine._closed_chunk(arena, rec_ptrs, lo, hi, t, 1, act[t:t + 1], 0, seed, st)
-                    if lag > 0 and t == min(lag, T) - 1 and g + 1 < G:
-                        gate = torch.cuda.Event()
-                        gate.record(st)
                 engine.observe(lo=lo, hi=hi)
                 h_fin = [hist_c[T - 1 + D][sl]] + hist_of(T - 1)[:D - 1]
                 scratch = torch.empty(hi - lo, N, E, dtype=torch.float32, device=dev)
