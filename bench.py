@@ -274,11 +274,28 @@ def cpu_policy_rollout(cfg, wl, n_envs, steps_T, seed=0):
     return dt, B * N * steps_T
 
 
+def use_all_host_threads():
+    """The CPU arm runs on every host thread this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers when the
+    variable is unset, which would silently make the N > 1 reference arm a one-thread run: set the count explicitly in the
+    environment (for runtimes not initialised yet), in the GNU OpenMP runtime the C oracle links, and in torch."""
+    import ctypes
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
 def cpu_policy_baseline(cfg, wl, steps_T, budget_s):
     """Bounded sample of the same workload on the host: sized from a short calibration so one pass is ~budget_s."""
     import torch
     from oracle import oracle as orc
     orc.build()
+    use_all_host_threads()
     cores = orc.num_threads()
     torch.set_num_threads(cores)
     n0 = min(32, len(wl["map_id"]))
