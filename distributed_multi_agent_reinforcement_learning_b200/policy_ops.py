@@ -3,6 +3,7 @@
 Only plain dense layers go through library GEMMs (torch.addmm / torch.mm -> cuBLAS); everything pairwise, sparse or
 pointwise is one of our kernels.  fp32 throughout (parity mode: TF32 is switched off for the GEMMs by the caller).
 """
+import collections
 import ctypes
 
 import torch
@@ -61,6 +62,9 @@ def _tc_ok(x, W, x2):
 
 
 USE_ROWGEMM = True          # persistent row-tile kernel (csrc/rowgemm_tf32x3.cu) when N, K1, K2 are multiples of 128
+ROWGEMM_MIN_ROWS = 256      # below: the tile-per-CTA kernel (a performance threshold only; tests lower both to exercise the
+WGRAD_MIN_ROWS = 2048       # production kernels on small fixtures)
+CALLS = collections.Counter()   # launches per tensor-core kernel family (tests assert the production path really ran)
 _PACK_CACHE = {}
 _PACK_SCOPE = [0]
 
@@ -96,7 +100,7 @@ def _packed_weight(W, N, K, stride_n, stride_k):
 
 
 def _rowgemm_ok(M, N, K1, K2):
-    return USE_ROWGEMM and N % 128 == 0 and N <= 512 and K1 % 128 == 0 and K2 % 128 == 0 and M >= 256
+    return USE_ROWGEMM and N % 128 == 0 and N <= 512 and K1 % 128 == 0 and K2 % 128 == 0 and M >= ROWGEMM_MIN_ROWS
 
 
 def _aligned_rows(t):
@@ -130,6 +134,7 @@ def _gemm_tc(x, x2, W, bias, add, relu, out=None, transposed=False):
         out = torch.empty(M, N, dtype=torch.float32, device=x.device)
     if _rowgemm_ok(M, N, K1, K2):
         packed = _packed_weight(W, N, K, stride_n, stride_k)
+        CALLS["rowgemm"] += 1
         _lib.check(_L().marl_rowgemm_tf32x3(
             M, N, K1, K2, x.data_ptr(), x.stride(0), x2.data_ptr() if x2 is not None else None, x2.stride(0) if x2 is not None else 0,
             packed.data_ptr(), bias.data_ptr() if bias is not None else None, add.data_ptr() if add is not None else None,
@@ -138,6 +143,7 @@ def _gemm_tc(x, x2, W, bias, add, relu, out=None, transposed=False):
         return out
     if transposed:
         W = W.t().contiguous()
+    CALLS["gemm_tile"] += 1
     _lib.check(_L().marl_gemm_tf32x3(
         M, N, K1, K - K1, x.data_ptr(), x.stride(0), x2.data_ptr() if x2 is not None else None,
         x2.stride(0) if x2 is not None else 0, W.data_ptr(), W.stride(0), bias.data_ptr() if bias is not None else None,
@@ -147,7 +153,7 @@ def _gemm_tc(x, x2, W, bias, add, relu, out=None, transposed=False):
 
 
 def _wgrad_ok(dy, x):
-    return (USE_TENSOR_CORES and dy.is_cuda and dy.dtype == torch.float32 and x.dtype == torch.float32 and dy.shape[0] >= 2048
+    return (USE_TENSOR_CORES and dy.is_cuda and dy.dtype == torch.float32 and x.dtype == torch.float32 and dy.shape[0] >= WGRAD_MIN_ROWS
             and dy.shape[1] % 128 == 0 and x.shape[1] % 128 == 0 and dy.stride(1) == 1 and x.stride(1) == 1)
 
 
@@ -159,12 +165,14 @@ def wgrad(dy, x, out=None, col0=0, dbias=None):
     if out is None:
         out = torch.empty(N, K, dtype=torch.float32, device=dy.device)
     if not _wgrad_ok(dy, x):
+        CALLS["wgrad_library"] += 1
         out[:, col0:col0 + K] = dy.t() @ x
         if dbias is not None:
             dbias.copy_(dy.sum(0))
         return out
     ws = torch.empty(int(_L().marl_wgrad_workspace_bytes(R, N, K)), dtype=torch.uint8, device=dy.device)
     dst = out[:, col0:]
+    CALLS["wgrad"] += 1
     _lib.check(_L().marl_wgrad_tf32x3(R, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dst.data_ptr(), out.stride(0),
                                       dbias.data_ptr() if dbias is not None else None, 0, ws.data_ptr(), _lib.stream_ptr()),
                "marl_wgrad_tf32x3")
@@ -269,6 +277,7 @@ def linear(x, W, bias=None, relu=False, x2=None, add=None):
     """act(cat([x, x2], 1) @ W.T + bias + add) for 2-D x; tensor-core path when the shape allows, library GEMM otherwise."""
     if _tc_ok(x, W, x2):
         return _LinearTC.apply(x, x2, W, bias, add, relu)
+    CALLS["linear_library"] += 1
     xin = x if x2 is None else torch.cat([x, x2], dim=1)
     out = torch.addmm(bias, xin, W.t()) if bias is not None else xin @ W.t()
     if add is not None:
@@ -347,6 +356,7 @@ class _GRULayer(torch.autograd.Function):
         if tc and E == 128 and USE_GRU_SEQ:
             # whole recurrence in one persistent kernel (csrc/gru_seq.cu)
             packed = _gru_pack(w_hh)
+            CALLS["gru_seq_fwd"] += 1
             _lib.check(_L().marl_gru_seq_fwd(T, R, E, gi_all.data_ptr(), h0.contiguous().data_ptr(), packed.data_ptr(),
                                              b_hh.contiguous().data_ptr(), out.data_ptr(), saves.data_ptr() if need else None,
                                              _lib.stream_ptr()), "marl_gru_seq_fwd")
@@ -382,6 +392,7 @@ class _GRULayer(torch.autograd.Function):
             dgh = torch.empty(T, R, 3 * E, dtype=x.dtype, device=x.device)
             dh0 = torch.empty(R, E, dtype=x.dtype, device=x.device)
             h0c = h0.contiguous()
+            CALLS["gru_seq_bwd"] += 1
             _lib.check(_L().marl_gru_seq_bwd(T, R, E, d_out.data_ptr(), saves.data_ptr(), out.data_ptr(), h0c.data_ptr(),
                                              packed.data_ptr(), dgi.data_ptr(), dgh.data_ptr(), dh0.data_ptr(), _lib.stream_ptr()),
                        "marl_gru_seq_bwd")

@@ -130,16 +130,34 @@ def gen_case(R, depth, n_def, T, episodes, mb, seed, emb=32):
     return fx
 
 
-def gen_algo():
+# (depth, pursuers, T, episodes, minibatch episodes, seed, embedding_dim).  The E = 128 cases pin training at the PRODUCTION width,
+# where every dense layer runs on the tcgen05 kernels (rowgemm / wgrad / gru_seq) instead of the library GEMMs the E = 32 cases
+# fall back to; 5 episodes with minibatches of 2 give 3 minibatches (the last one ragged), so the running clip matters.
+CASES = ((1, 4, 10, 3, 2, 21, 32), (3, 5, 8, 3, 2, 23, 32), (1, 8, 20, 5, 2, 25, 128), (3, 5, 16, 5, 2, 27, 128))
+
+
+def gen_algo(only_emb=None):
     R = load_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for depth, n_def, T, episodes, mb, seed in ((1, 4, 10, 3, 2, 21), (3, 5, 8, 3, 2, 23)):
-        fx = gen_case(R, depth, n_def, T, episodes, mb, seed)
-        path = os.path.join(GOLDEN_DIR, f"algo_d{depth}_n{n_def}.npz")
+    for depth, n_def, T, episodes, mb, seed, emb in CASES:
+        if only_emb is not None and emb != only_emb:
+            continue
+        fx = gen_case(R, depth, n_def, T, episodes, mb, seed, emb)
+        if emb != 32:
+            # keep the wide fixtures small: the encoder is ONE module shared by both networks, so its critic.* copies (weights and
+            # gradients) are dropped after checking they are identical, and the weights after the optimizer step are not stored
+            # (the reference's optimizer is stock torch.optim.Adam(eps=1e-5): the test re-runs it on the stored gradients)
+            for k in [k for k in fx if ".critic.shared_net." in k]:
+                twin = k.replace(".critic.", ".actor.")
+                assert np.array_equal(fx[k], fx[twin]), k
+                del fx[k]
+            for k in [k for k in fx if k.startswith("w_after.")]:
+                del fx[k]
+        path = os.path.join(GOLDEN_DIR, f"algo_d{depth}_n{n_def}" + ("" if emb == 32 else f"_e{emb}") + ".npz")
         np.savez_compressed(path, **fx)
-        print(f"algo depth={depth} N={n_def}: objC={float(fx['objC']):.6f} objA={float(fx['objA']):.6f} "
+        print(f"algo depth={depth} N={n_def} E={emb}: objC={float(fx['objC']):.6f} objA={float(fx['objA']):.6f} "
               f"minibatches={int(fx['n_mb'])} file={os.path.getsize(path) / 1e6:.2f} MB")
 
 
 if __name__ == "__main__":
-    gen_algo()
+    gen_algo(int(sys.argv[1]) if len(sys.argv) > 1 else None)

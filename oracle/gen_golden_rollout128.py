@@ -47,9 +47,15 @@ def gen(R, depth, n_def, T, episodes, seed):
     return fx
 
 
-def main():
+# the N = 16 case runs the 8-worker-warp variant of the fused kernel (a whole 16-agent env per warp, BASELINE configs[2])
+CASES = ((1, 8, 6, 3, 31), (3, 5, 7, 2, 33), (3, 16, 6, 2, 35))
+
+
+def main(only_n=None):
     R = load_reference()
-    for depth, n_def, T, episodes, seed in ((1, 8, 6, 3, 31), (3, 5, 7, 2, 33)):
+    for depth, n_def, T, episodes, seed in CASES:
+        if only_n is not None and n_def != only_n:
+            continue
         fx = gen(R, depth, n_def, T, episodes, seed)
         path = os.path.join(GOLDEN_DIR, f"rollout128_d{depth}_n{n_def}.npz")
         np.savez_compressed(path, **fx)
@@ -57,4 +63,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else None)

@@ -9,13 +9,13 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_DIR
+from conftest import GOLDEN_DIR, AlgoFixture
 
 FIXTURES = sorted(glob.glob(os.path.join(GOLDEN_DIR, "algo_*.npz")))
 
 
 def load_algo(path):
-    fx = np.load(path)
+    fx = AlgoFixture(path)
     w = {k[2:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("w.")}
     buf = {k[4:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("buf.")}
     return fx, w, buf
