@@ -10,8 +10,9 @@ rollout arena, i.e. MAPPO.run_episode (DHGN/mappo_parallel.py:742-827) for all e
 metric = agent-env-steps/s = B*N*T / time, whole job (all ranks).
   value : episode replayed from HBM-resident initial state (one CUDA graph of the whole episode).
   env_only / train : secondary numbers (env-only closed loop with scripted random actions; one PPO epoch).
-  e2e   : same episode through the public API with HOST buffers: pinned initial states/targets H2D + episode
-          reward sums D2H inside the timed region.
+  e2e   : same episode through the public per-iteration call `MAPPO.explore_batched(engine, arena, host_state=..., host_out=...)`
+          with HOST buffers: pinned initial states/targets H2D + per-env episode reward sums / collision flags D2H inside the
+          timed region.
 --impl reference : the CPU port of the same loop (oracle/marl_oracle.c env with OpenMP + the torch-CPU restatement of
           the networks, all host threads) on a bounded sample of the same workload.
 """
@@ -338,31 +339,33 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-class PolicyEpisodeGraph:
-    """MAPPO.run_episode for all envs (network in the loop) captured as ONE CUDA graph: per env step
-    observe -> fused policy step (encoder + GRU + heads of both networks, ONE launch) -> A* replan when due ->
-    fused evader-move/step/reward-norm/store kernel; 3-4 kernels per step, no host involvement on replay."""
+def policy_flops_split(N, O_actor, O_critic, D, head=2304):
+    """SURVEY 8(d) per-agent forward FLOPs, split: (gemm-only per network [the 128-wide dense layers + heads: what the tensor
+    cores execute], actor messages / aggregation with O_actor obstacle slots, same for the critic with O_critic)."""
+    gemm = 3 * 32768 + 99328 + D * 98304 + 393216 + head
+    msg = lambda O: 2048 * N + 1024 + 1024 * O + 256 * (N + 1 + O) + D * 256 * N
+    return gemm, msg(O_actor), msg(O_critic)
 
-    def __init__(self, torch, mappo, env, arena, T, seed):
-        from distributed_multi_agent_reinforcement_learning_b200 import _lib
-        self.env, self.snap = env, env.snapshot()
-        mappo.rollout_batched(env, arena, T, seed=seed)           # eager warm-up (cuBLAS handles, kernel attributes)
-        torch.cuda.synchronize()
-        env.restore(self.snap)
-        self.graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        c0 = _lib.CALLS
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(self.graph, stream=side):
-                self.batch = mappo.rollout_batched(env, arena, T, seed=seed)
-        self.our_launches = _lib.CALLS - c0
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        env.restore(self.snap)
 
-    def replay(self):
-        self.graph.replay()
+def train_bytes_per_sample(D):
+    """Algorithmic HBM bytes of one PPO training sample (one agent-step, BOTH networks) for the layer-by-layer schedule that
+    `MAPPO.train` runs: every layer reads its input rows once and writes its output rows once in the forward
+    pass; the backward pass reads each saved activation and each upstream gradient once and writes each downstream gradient once
+    (dX and dW share one read of dY only inside the GRU sequence kernel).  Unit = one 128-float row (512 B), per network:
+      forward : messages 3 w | AGG_vertex 3 r + 3 w | semantic 3 r + 1 w (+ 2 for the state term) | per depth: neighbour mean 1 r + 1 w,
+                AGG_fcra 1 r + 1 w, FCRA 2 r + 1 w | per GRU layer: input projection 1 r + 3 w, recurrence 3 r + 1 w + 4 saves | head 1 r
+      backward: 2 x forward (dX pass + dW pass over the same rows)."""
+    fwd_rows = 3 + 6 + 6 + D * 7 + 2 * 12 + 1
+    return 2 * 3 * fwd_rows * 512
+
+
+def _popcount_mean(torch, words):
+    """Mean number of set bits per row of a packed int32 [..., W] tensor."""
+    w = words.to(torch.int64) & 0xFFFFFFFF
+    cnt = torch.zeros(w.shape[:-1], dtype=torch.float64, device=w.device)
+    for b in range(32):
+        cnt += ((w >> b) & 1).sum(-1)
+    return cnt.mean().item()
 
 
 def run_ours(args):
@@ -398,13 +401,26 @@ def run_ours(args):
     torch.manual_seed(0xB200)
     mappo = MAPPO(cfg, B, max(1, round(B / 10)), "Learner")      # mini_batch = round(workers/10) (main.py:48)
     mappo.sync_weights(0)
-    pol = PolicyEpisodeGraph(torch, mappo, env, arena, T, seed=0xB200 + rank)
+    SEED = 0xB200 + rank
+    mappo.explore_batched(env, arena, T, seed=SEED)                # the public call; its first use captures the episode graph
+    torch.cuda.synchronize()
+    env.restore(snap)
+    pol = mappo._episode_graphs[(id(env), id(arena), T, SEED)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def per_rank(ms):
+        """[rank 0 .. rank N-1] of a per-rank time: the whole-job number is quoted on the slowest one."""
+        t = torch.tensor([float(ms)], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(ms)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(x.item()) for x in out]
 
     def timed(fn, n_iter, before=None):
         total = 0.0
@@ -432,6 +448,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     status = int(env.evader_status.max().item())
     assert status == 0, f"evader status {status}: search overflow or target tape exhausted"
+    per_rank_ms = {"value": [x / args.steps for x in per_rank(ms_total)]}
     ms_total = parallel.max_over_ranks(ms_total, dev)
     value = world * B * N * T * args.steps / (ms_total * 1e-3)
 
@@ -441,23 +458,19 @@ def run_ours(args):
     coll_host = torch.zeros(B, dtype=torch.uint8).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in pin.values())
     d2h = ep_reward_host.numel() * 8 + coll_host.numel()
-    zero_names = ("path_len", "time_step", "collision", "done", "tape_pos", "evader_status", "wf_n", "wf_mean", "wf_S", "wf_std")
 
-    def e2e_episode(graph):
-        env.p_state.copy_(pin["p_state"], non_blocking=True)
-        env.e_state.copy_(pin["e_state"], non_blocking=True)
-        env.target.copy_(pin["target"], non_blocking=True)
-        for n_ in zero_names:
-            getattr(env, n_).zero_()
-        graph.replay()
-        ep_reward_host.copy_(arena.raw_reward.sum(dim=(0, 2), dtype=torch.int64), non_blocking=True)
-        coll_host.copy_(env.collision, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    host_state = {k: pin[k] for k in ("p_state", "e_state", "target")}
+    host_out = {"episode_reward": ep_reward_host, "collision": coll_host}
 
-    timed(lambda: e2e_episode(pol), args.warmup)
+    def e2e_episode():
+        # the public per-iteration call with HOST buffers: H2D of the initial state, the whole episode, D2H of the per-env results
+        mappo.explore_batched(env, arena, T, seed=SEED, host_state=host_state, host_out=host_out, reset_reward_norm=True)
+
+    timed(e2e_episode, args.warmup)
     barrier()
-    e2e_ms = timed(lambda: e2e_episode(pol), args.steps)
+    e2e_ms = timed(e2e_episode, args.steps)
     barrier()
+    per_rank_ms["e2e"] = [x / args.steps for x in per_rank(e2e_ms)]
     e2e_value = world * B * N * T * args.steps / (parallel.max_over_ranks(e2e_ms, dev) * 1e-3)
 
     # ---- secondary: env-only closed loop (scripted random policy), as in the survey's env-only probe ------------
@@ -465,7 +478,9 @@ def run_ours(args):
     env_graph = EpisodeGraph(env, arena, T, seed=0xB200 + rank, groups=STREAM_GROUPS)
     timed(env_graph.replay, 2, restore)
     barrier()
-    env_ms = parallel.max_over_ranks(timed(env_graph.replay, max(3, args.steps // 2), restore), dev) / max(3, args.steps // 2)
+    env_ms_local = timed(env_graph.replay, max(3, args.steps // 2), restore) / max(3, args.steps // 2)
+    per_rank_ms["env_only"] = per_rank(env_ms_local)
+    env_ms = parallel.max_over_ranks(env_ms_local, dev)
     env_only = {"value": world * B * N * T / (env_ms * 1e-3), "unit": UNIT, "ms_per_episode": env_ms,
                 "policy": "uniform random actions (device counter RNG)", "stream_groups": STREAM_GROUPS}
 
@@ -482,43 +497,122 @@ def run_ours(args):
     train_epoch()
     barrier()
     n_train = max(1, min(3, args.steps))
-    tr_ms = parallel.max_over_ranks(timed(train_epoch, n_train), dev) / n_train
+    tr_ms_local = timed(train_epoch, n_train) / n_train
+    per_rank_ms["train"] = per_rank(tr_ms_local)
+    tr_ms = parallel.max_over_ranks(tr_ms_local, dev)
+    hbm_peak, peak_src = measured_peaks()
+    tensor_peak = measured_tensor_peak()
+    D = int(cfg.algo.depth)
+    o_b = float(torch.clamp(env.boundary_count, max=env.O).float()[env.map_id.long()].mean())      # real boundary cells per env
+    gemm_f, msg_a_all, msg_c_all = policy_flops_split(N, env.O, env.O, D)
+    tr_bytes = train_bytes_per_sample(D) * B * T * N
+    tr_flops = 3 * (2 * gemm_f + msg_a_all + msg_c_all) * B * T * N            # forward + dX + dW passes; training pads to all O slots
     train = {"samples_per_sec": world * B * T * N / (tr_ms * 1e-3), "unit": "samples/s", "ms_per_epoch": tr_ms,
              "minibatches": -(-B // mappo.mini_batch_size), "dtype": "f32 (TF32 off)",
-             "allreduce": "1 x SUM over the flat gradient arena (%d floats)" % mappo.ac_optimizer.flat_grad.numel()}
+             "allreduce": "1 x SUM over the flat gradient arena (%d floats) per update; train(allreduce='minibatch') = 1 per PPO minibatch"
+                          % mappo.ac_optimizer.flat_grad.numel(),
+             "roofline": {"bound": "hbm", "achieved": tr_bytes / (tr_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": tr_bytes / (tr_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                          "algorithmic_bytes_per_sample": train_bytes_per_sample(D),
+                          "bytes_model": "layer-by-layer schedule: each layer reads its input rows and writes its output rows once "
+                                         "forward, twice that backward (bench.train_bytes_per_sample; DESIGN.md section 5)",
+                          "tensor_TFLOPs": tr_flops / (tr_ms * 1e-3) / 1e12, "tensor_frac": tr_flops / (tr_ms * 1e-3) / 1e12 / tensor_peak,
+                          "peak_source": peak_src}}
 
-    # ---- per-kernel durations: CUDA events around every launch of ONE eager network-in-the-loop episode (same stream) -----
+    # ---- per-kernel durations (1): CUDA events around every launch of ONE eager, single-pipeline episode (same stream) -----
     env.restore(snap)
     timers = {}
-    mappo.rollout_batched(env, arena, T, seed=0xB200 + rank, timers=timers)
+    mappo.rollout_batched(env, arena, T, seed=SEED, timers=timers)
     torch.cuda.synchronize()
     kernel_table = {k: {"launches": len(v), "total_ms": sum(a.elapsed_time(b) for a, b in v)} for k, v in timers.items()}
     for v in kernel_table.values():
         v["avg_us"] = 1e3 * v["total_ms"] / v["launches"]
+    # ---- per-kernel durations (2): the same events inside the schedule that `value` times - G env-group pipelines on G streams.
+    # A group's policy launch is timed on its own stream; launches of different groups overlap, so the kernel's time per episode
+    # is the UNION of its launch intervals (<= the episode's wall time by construction).
+    G = MAPPO.default_pipelines(B, N)
+    pk = kernel_table["policy_step_kernel"]
+    pipe = None
+    if G > 1:
+        # The SAME graph-captured pipelined schedule once more, every policy launch writing its per-CTA %globaltimer start / end
+        # and SM id (the kernel's profiling record): a launch's interval is [first CTA start, last CTA end]; launches of different
+        # env groups overlap, so the kernel's time per episode is the UNION of the intervals (<= the episode's wall time).
+        from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import RolloutGraph
+        full_tile = (128 // N) * N
+        ctas = 2 * (-(-(B // G) * N // full_tile) + 1)
+        dbg = torch.zeros(T, G, ctas, 16, dtype=torch.int64, device=dev)
+        env.restore(snap)
+        ig = RolloutGraph(mappo, env, arena, T, SEED, policy_dbg=dbg)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            env.restore(snap)
+            dbg.zero_()
+            flush.fill_(1)
+            ev0.record()
+            ig.replay()
+            ev1.record()
+            torch.cuda.synchronize()
+        wall = ev0.elapsed_time(ev1)
+        rec = dbg.cpu().numpy()
+        used = rec[..., 14] > 0
+        starts = np.where(used, rec[..., 13], np.iinfo(np.int64).max).min(axis=2)      # [T, G] ns
+        ends = np.where(used, rec[..., 14], 0).max(axis=2)
+        iv = sorted(zip(starts.reshape(-1).tolist(), ends.reshape(-1).tolist()))
+        union, cs, ce = 0, None, None
+        for a_, b_ in iv:
+            if ce is None or a_ > ce:
+                union += (ce - cs) if ce is not None else 0
+                cs, ce = a_, b_
+            else:
+                ce = max(ce, b_)
+        union += (ce - cs) if ce is not None else 0
+        cta_busy_ns = float(np.where(used, rec[..., 14] - rec[..., 13], 0).sum())
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        pipe = {"pipelines": G, "instrumented_graph_episode_ms": wall, "policy_launches": int(starts.size),
+                "policy_group_launch_avg_us": float((ends - starts).mean()) * 1e-3,
+                "policy_union_ms": union * 1e-6, "policy_share_of_episode": union * 1e-6 / wall,
+                "policy_sm_busy_ms": cta_busy_ns * 1e-6 / n_sm,
+                "note": "per-CTA %globaltimer records written by policy_step_kernel inside the graph-captured pipelined schedule; "
+                        "union = time during which at least one policy launch is executing; sm_busy = sum of CTA lifetimes / SMs"}
     env.restore(snap)
     ms_episode = ms_total / args.steps
-    hbm_peak, peak_src = measured_peaks()
-    tensor_peak = measured_tensor_peak()
-    pk = kernel_table["policy_step_kernel"]
-    flops_launch = 2 * policy_flops_per_agent(N, env.O, cfg.algo.depth) * B * N        # actor + critic
-    achieved = flops_launch / (pk["avg_us"] * 1e-6) / 1e12
+    flops_pp = policy_flops_per_agent(N, env.O, D)
+    flops_launch = 2 * flops_pp * B * N                                       # actor + critic, SURVEY 8(d) upper bound (all O slots)
+    # executed obstacle work: the actor touches only visible cells, the critic the O_b real boundary cells of the map
+    o_vis = float(_popcount_mean(torch, pol.batch.o_adj_bits))
+    _, msg_a_exec, msg_c_exec = policy_flops_split(N, o_vis, o_b, D)
+    flops_exec_launch = (2 * gemm_f + msg_a_exec + msg_c_exec) * B * N
+    # headline rate: on the timed region itself - the episode's policy FLOPs over the driver-timed episode (a lower bound of the
+    # kernel's own rate: the episode also contains the env / A* kernels), and over the union of the kernel's launch intervals
+    policy_ms = pipe["policy_union_ms"] * min(1.0, ms_episode / pipe["instrumented_graph_episode_ms"]) if pipe else pk["total_ms"]
+    policy_ms = min(policy_ms, ms_episode)
+    achieved = flops_launch * (T + 1.0 / 2) / (policy_ms * 1e-3) / 1e12       # T two-network launches + the bootstrap critic launch
+    achieved_step = flops_launch * (T + 1.0 / 2) / (ms_episode * 1e-3) / 1e12
     # HBM traffic the fused kernel needs per launch: state/adjacency in, history in, embedding + hidden (r/w) + heads out
-    bytes_launch = B * N * (32 + 4 + 1 + 24 + 2 * (cfg.algo.depth * 512 + 512 + 4 * 512) + 12)
-    roofline = {"kernel": "policy_step_kernel (DHGN encoder + 2-layer GRU + heads of actor AND critic, one launch per env step; "
+    bytes_launch = B * N * (32 + 4 + 1 + 24 + 2 * (D * 512 + 512 + 4 * 512) + 12)
+    roofline = {"kernel": "policy_step_kernel (DHGN encoder + 2-layer GRU + heads of actor AND critic, one launch per env step and env group; "
                           "tcgen05 kind::f16 on a two-term fp16 split of both operands, 3 products per K step for fp32-level accuracy, "
                           "accumulators in TMEM)",
                 "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                "traffic": 144.9e6, "traffic_source": "profiles/r1_policy_step_kernel_ncu_summary.txt (dram read + write of one launch, ncu --set full)",
+                "traffic": None,
+                "traffic_note": "not measured in this run; profiles/ holds the dram bytes of one launch from the ncu --set full capture",
+                "timing": "in-kernel %globaltimer records of every policy launch inside the graph-captured pipelined schedule that `value` "
+                          "times (a second, instrumented capture of the same schedule); kernel time per episode = union of the launch "
+                          "intervals",
+                "policy_ms_per_episode": policy_ms, "ms_per_step": ms_episode,
+                "frac_on_timed_episode": achieved_step / tensor_peak,
+                "frac_gemm_only": (2 * gemm_f * B * N) * (T + 0.5) / (policy_ms * 1e-3) / 1e12 / tensor_peak,
+                "frac_executed": flops_exec_launch * (T + 0.5) / (policy_ms * 1e-3) / 1e12 / tensor_peak,
+                "executed_obstacle_slots": {"actor_visible_mean": o_vis, "critic_boundary_mean": o_b, "survey_upper_bound": env.O},
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16 = the kind::f16 rate; the split issues 3 MMAs "
                                "per algorithmic product, so this kernel's ceiling is frac = 1/3)",
-                "algorithmic_flops_per_launch": flops_launch, "flops_per_agent_per_network": policy_flops_per_agent(N, env.O, cfg.algo.depth),
-                "avg_launch_us": pk["avg_us"], "share_of_step": pk["total_ms"] / sum(v["total_ms"] for v in kernel_table.values()),
-                "share_note": "share of the kernel time of one eager, single-pipeline episode (kernel_ms_per_episode); the timed episode is "
-                              "one CUDA graph of 4 env-group pipelines whose kernels overlap, so its wall time is below that sum",
+                "algorithmic_flops_per_launch": flops_launch, "flops_per_agent_per_network": flops_pp,
+                "gemm_flops_per_agent_per_network": gemm_f,
+                "single_pipeline_avg_launch_us": pk["avg_us"], "pipelined": pipe,
                 "hbm_bytes_per_launch_algorithmic": bytes_launch,
-                "hbm_GBps_at_this_duration": bytes_launch / (pk["avg_us"] * 1e-6) / 1e9, "hbm_peak_GBps": hbm_peak,
-                "note": "SURVEY 8(d) FLOP count per agent and network (obstacle messages counted for all O slots: upper bound) x "
-                        "B*N rows x 2 networks per launch"}
+                "hbm_GBps_at_this_duration": bytes_launch * (T + 0.5) / (policy_ms * 1e-3) / 1e9, "hbm_peak_GBps": hbm_peak,
+                "note": "SURVEY 8(d) FLOP count per agent and network (obstacle messages counted for all O slots: upper bound; "
+                        "frac_executed counts the slots really evaluated, frac_gemm_only the dense layers only) x B*N rows x 2 networks"}
 
     if rank == 0:
         # ---- CPU baseline: oracle port (C env + torch-CPU network restatement) on the host cores, bounded sample ----
@@ -529,7 +623,8 @@ def run_ours(args):
             "dtype": "f64 env / f32 networks", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": pol.our_launches * args.steps, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "env_only": env_only, "train": train, "kernel_ms_per_episode": kernel_table}))
+            "cpu_baseline": cpu, "env_only": env_only, "train": train, "per_rank_ms": per_rank_ms,
+            "kernel_ms_per_episode": kernel_table}))
     if world > 1:
         dist.destroy_process_group()
 

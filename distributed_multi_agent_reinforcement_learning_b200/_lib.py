@@ -157,11 +157,18 @@ def check(rc, what=""):
 
 
 def ptr(t):
-    """Device (or host) address of a torch tensor / None -> NULL.  Tensors must be contiguous."""
+    """Device (or host) address of a torch tensor / None -> NULL.  Tensors must be contiguous, and device tensors must live on
+    the CURRENT device: the kernels are launched on the current device's stream (one process per GPU; a rank that forgot
+    `torch.cuda.set_device` would otherwise launch on cuda:0 with another device's pointers)."""
     if t is None:
         return None
     if not t.is_contiguous():
         raise MarlError("non-contiguous tensor passed to the C-ABI")
+    if t.is_cuda:
+        import torch
+        if t.device.index != torch.cuda.current_device():
+            raise MarlError(f"tensor on {t.device} passed to a launch on cuda:{torch.cuda.current_device()}: call "
+                            "torch.cuda.set_device(...) (or wrap the call in torch.cuda.device(...)) first")
     return t.data_ptr()
 
 

@@ -6,7 +6,8 @@
 * `Evaluator` — the bookkeeping of `EvaluatorProc` (evaluator.py:20-103): `run`, `evaluate_and_save`, `recorder` rows
   `(total_step, avg_r, std_r, exp_r, *logging_tuple)`, "save when the average return does not get worse".  Its episodes are
   ONE batched arg-max rollout of `num_cpus_eval` independent environments on the GPU (`MAPPO.rollout_batched(deterministic=
-  True)`) instead of `num_cpus_eval` Ray tasks.
+  True, actor_only=True)`: the actor alone, fed with its own previous embeddings exactly as `evaluate` does) instead of
+  `num_cpus_eval` Ray tasks.
 """
 import time
 
@@ -95,7 +96,7 @@ class Evaluator:
         eng, T = self._engine, int(cfg.env.max_steps)
         self._seed += 1
         eng.reset_device(seed=self._seed, tape_len=64)
-        self.agent.rollout_batched(eng, self._arena, T, seed=self._seed, deterministic=True)
+        self.agent.rollout_batched(eng, self._arena, T, seed=self._seed, deterministic=True, actor_only=True)
         ret = self._arena.raw_reward[:T].sum(dim=(0, 2)).to(torch.float32)
         steps = torch.full((B,), float(T - 1), dtype=torch.float32, device=ret.device)   # `done` fires at step index T-1
         return torch.stack([ret, steps], dim=1).cpu()

@@ -343,6 +343,32 @@ class TrainBatch:
                         v=s(self.v), a=s(self.a), logp=s(self.logp), r=s(self.r), active=s(self.active), depth=self.depth)
         return mb
 
+    def minibatch_indexed(self, index):
+        """Envs `index` (int64 device tensor, any order): the reference's `batch[key][index]` (:665-679) for an arbitrary index list,
+        every slab gathered by `marl_gather_rows` (one launch per tensor: row = one env at one step, source row t*B + index[b])."""
+        T, B = self.T, self.B
+        index = index.to(torch.int64).contiguous()
+        mb = index.numel()
+        rows = {}
+
+        def g(x, lead_t=True):
+            x = x.contiguous()
+            Tx = x.shape[0] if lead_t else 1
+            if Tx not in rows:          # source row of (t, b) in the [Tx*B, row] view of a time-major slab
+                rows[Tx] = ((torch.arange(Tx, device=x.device, dtype=torch.int64) * B).unsqueeze(1) + index.unsqueeze(0)).reshape(-1).contiguous()
+            idx = rows[Tx]
+            tail = tuple(x.shape[2:]) if lead_t else tuple(x.shape[1:])
+            out = torch.empty(((Tx, mb) if lead_t else (mb,)) + tail, dtype=x.dtype, device=x.device)
+            row_bytes = (x.numel() // (Tx * B)) * x.element_size()
+            _lib.check(_lib.lib().marl_gather_rows(x.data_ptr(), out.data_ptr(), idx.data_ptr(), idx.numel(), row_bytes, Tx * B,
+                                                   _lib.stream_ptr()), "marl_gather_rows")
+            return out
+
+        return TrainBatch(p=g(self.p), e=g(self.e), oxy=g(self.oxy, False), o_count_train=g(self.o_count_train, False),
+                          p_adj_bits=g(self.p_adj_bits), e_adj=g(self.e_adj), o_adj_bits=g(self.o_adj_bits), hist_a=g(self.hist_a),
+                          hist_c=g(self.hist_c), v=g(self.v), a=g(self.a), logp=g(self.logp), r=g(self.r), active=g(self.active),
+                          depth=self.depth), g
+
     def graph(self):
         T, B, N = self.T, self.B, self.N
         o_index = torch.arange(B, dtype=torch.int32, device=self.p.device).repeat(T)
@@ -357,6 +383,35 @@ class TrainBatch:
         D, T, B, N = self.depth, self.T, self.B, self.N
         E = h.shape[-1]
         return [(h[D - 1 - k:], N * E, E) for k in range(D)]
+
+
+class RolloutGraph:
+    # (policy_dbg: see MAPPO._rollout_pipelined - an instrumented capture for measurements, not for production replays)
+    """`MAPPO.rollout_batched` for all envs of an engine (networks in the loop) captured as ONE CUDA graph: per env step
+    observe -> fused policy step (encoder + GRU + heads of both networks, one launch per env group) -> A* replan when due ->
+    fused evader-move / step / reward-norm / store kernel; no host involvement on replay.  The engine state the episode starts
+    from is whatever the engine holds at replay time."""
+
+    def __init__(self, mappo, engine, arena, T, seed, policy_dbg=None):
+        snap = engine.snapshot()
+        kw = {} if policy_dbg is None else dict(timers={"_policy_dbg": policy_dbg}, pipelines=policy_dbg.shape[1])
+        mappo.rollout_batched(engine, arena, T, seed=seed)           # eager warm-up (kernel attributes, stream pool)
+        torch.cuda.synchronize()
+        engine.restore(snap)
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        c0 = _lib.CALLS
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(self.graph, stream=side):
+                self.batch = mappo.rollout_batched(engine, arena, T, seed=seed, **kw)
+        self.our_launches = _lib.CALLS - c0                           # C-ABI calls (>= 1 of our kernels each) per replay
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        engine.restore(snap)
+
+    def replay(self):
+        self.graph.replay()
 
 
 class MAPPO:
@@ -378,7 +433,7 @@ class MAPPO:
         if not self.use_value_clip:
             raise NotImplementedError("use_value_clip=False is not wired into the fused head kernel")
         if a.use_reward_norm:
-            self.reward_norm = Normalization(shape=cfg.env.num_defender)
+            self.reward_norm = Normalization(shape=cfg.env.num_defender, device=self.device)
         encoder = DHGN(self.input_dim, self.embedding_dim, self.sn, a, self.device)
         self.depth = a.depth
         self.actor = SharedActor(encoder, self.rnn_input_dim, self.action_dim, self.num_layers, self.rnn_hidden_dim, self.sn)
@@ -444,9 +499,22 @@ class MAPPO:
                               _lib.ptr(vt), _lib.ptr(ws), _lib.stream_ptr()), "marl_gae")
         return adv, vt
 
-    def train(self, replay_buffer, total_steps, return_numpy=True, trace=None):
+    def train(self, replay_buffer, total_steps, return_numpy=True, trace=None, allreduce=None, mean=False, shuffle=None,
+              shuffle_seed=None, permutation=None):
         """MAPPO.train (:638-723): GAE, then for each sequential minibatch forward / PPO losses / backward with gradients
-        accumulating and the global-norm clip applied to the running accumulation; no optimizer step here."""
+        accumulating and the global-norm clip applied to the running accumulation; no optimizer step here.
+
+        allreduce: None (default, the reference's protocol: the accumulated gradients are summed across replicas once per update,
+        in `update()` - main.py:121-129) or "minibatch" (north star: ONE all-reduce per PPO minibatch - every minibatch's gradient
+        is summed over the replicas (`mean=True`: averaged) before it enters the running, clipped accumulation, so the clip acts on
+        the global gradient and all replicas leave `train` with identical gradients; `update()` then only steps).
+        shuffle (default `cfg.algo.shuffle_minibatches`, false = the reference's SequentialSampler :665): minibatches are drawn from a
+        device permutation of the envs (seeded by `shuffle_seed`, or given as `permutation`) and gathered by `marl_gather_rows`."""
+        if allreduce not in (None, "update", "minibatch"):
+            raise ValueError(f"allreduce={allreduce!r}: None / 'update' (one all-reduce per update) or 'minibatch'")
+        per_mb = allreduce == "minibatch"
+        if shuffle is None:
+            shuffle = bool(getattr(self.cfg.algo, "shuffle_minibatches", False)) or permutation is not None
         data = replay_buffer.get_training_data(self.device) if hasattr(replay_buffer, "get_training_data") else replay_buffer
         tb = data if isinstance(data, TrainBatch) else TrainBatch.from_reference(data, self.depth)
         adv, v_target = self.gae(tb)
@@ -463,6 +531,18 @@ class MAPPO:
         # for the launch-latency-bound GRU sequence kernels.
         starts = list(range(0, bs, mbs))
         n_mb = len(starts)
+        perm = None
+        if shuffle:
+            if permutation is not None:
+                perm = torch.as_tensor(permutation, dtype=torch.int64, device=self.device)
+                if perm.numel() != bs or not torch.equal(torch.sort(perm).values, torch.arange(bs, device=self.device)):
+                    raise ValueError("permutation must be a permutation of range(batch_size)")
+            else:
+                gen = torch.Generator(device=self.device)
+                gen.manual_seed(int(total_steps) if shuffle_seed is None else int(shuffle_seed))
+                perm = torch.randperm(bs, device=self.device, generator=gen)
+            if trace is not None:
+                trace["permutation"] = perm.clone()
         flat = self.ac_optimizer.flat_grad
         views = self.ac_optimizer._views
         gbuf = torch.zeros(n_mb, flat.numel(), dtype=torch.float32, device=self.device)
@@ -477,8 +557,13 @@ class MAPPO:
                 st, side = self._mb_streams[m % P]
                 st.wait_stream(main)
                 with torch.cuda.stream(st):
-                    mb = tb.minibatch(lo, hi)
-                    la, lc, logp, ent, val = self._forward_losses(mb, adv[:, lo:hi].contiguous(), v_target[:, lo:hi].contiguous(), side=side)
+                    if perm is None:
+                        mb = tb.minibatch(lo, hi)
+                        adv_mb, vt_mb = adv[:, lo:hi].contiguous(), v_target[:, lo:hi].contiguous()
+                    else:
+                        mb, gather = tb.minibatch_indexed(perm[lo:hi])
+                        adv_mb, vt_mb = gather(adv), gather(v_target)
+                    la, lc, logp, ent, val = self._forward_losses(mb, adv_mb, vt_mb, side=side)
                     grads = torch.autograd.grad(la + lc, self.ac_parameters, allow_unused=True)
                     for g, (off, k) in zip(grads, views):
                         if g is not None:
@@ -489,11 +574,17 @@ class MAPPO:
                     del grads, la, lc, logp, ent, val, mb
             for st, _ in self._mb_streams[:P]:
                 main.wait_stream(st)
+            if trace is not None:
+                trace["mb_grads"] = gbuf.clone()            # this replica's per-minibatch gradients, before any reduction
             for m in range(n_mb):                           # gradients accumulate; clip_grad_norm_ acts on the running sum
+                if per_mb:                                  # one all-reduce per PPO minibatch: the clip then sees the global gradient
+                    from . import parallel
+                    parallel.allreduce_sum_(gbuf[m], mean=mean)
                 flat.add_(gbuf[m])
                 if self.use_grad_clip:
                     ops.clip_grad_norm_(flat, 5.0)
         self.ac_optimizer._sync_grads()
+        self._grads_reduced = per_mb
         lh = losses.cpu()
         if trace is not None:
             for m, rec in enumerate(trace["mb"]):
@@ -518,7 +609,9 @@ class MAPPO:
         """Learner.set_gradients_and_update across replicas (main.py:121-129, runner.py:72-78): ONE all-reduce (SUM) of
         the flat gradient arena over NCCL, then the same fused Adam step on every replica."""
         from . import parallel
-        parallel.allreduce_sum_(self.ac_optimizer.flat_grad, mean=mean)
+        if not getattr(self, "_grads_reduced", False):    # train(allreduce="minibatch") already reduced every minibatch's gradient
+            parallel.allreduce_sum_(self.ac_optimizer.flat_grad, mean=mean)
+        self._grads_reduced = False
         self.ac_optimizer.step()
         if self.use_lr_decay:
             self.lr_decay(total_steps)
@@ -536,11 +629,14 @@ class MAPPO:
     # ------------------------------------------------------------------------------------------------ rollout
     @torch.no_grad()
     def rollout_batched(self, engine, arena, T=None, seed=0, deterministic=False, groups=1, use_fused=None, timers=None,
-                        pipelines=None):
+                        pipelines=None, actor_only=False):
         """MAPPO.run_episode (:742-827) for all B envs of a BatchedPursuitEnv at once, entirely on the GPU.
         Per step: observe kernel -> fused encoder (actor, then critic with all-ones adjacency) -> GRU cell -> heads ->
         closed-loop env kernel (evader move + pursuer step + reward-norm + store).  Fills `arena` plus the history /
-        value / log-prob slabs and returns a TrainBatch ready for `train`."""
+        value / log-prob slabs and returns a TrainBatch ready for `train`.
+
+        actor_only=True is the EVALUATOR's episode (evaluator.py:118-156): no critic, and the actor's history is its OWN
+        embeddings A(t-1), A(t-2), ... (its dataset is not aliased with a critic's there); values / bootstrap stay zero."""
         T = T or arena.T
         B, N, E, D, L = engine.B, engine.N, self.embedding_dim, self.depth, self.num_layers
         dev = self.device
@@ -560,8 +656,8 @@ class MAPPO:
             # one aliased list for both nets (:750-752): newest first = C(t-1), A(t-1), C(t-2), A(t-2), ...
             out = []
             for k in range(D):
-                back = k // 2 + 1
-                src = hist_c if k % 2 == 0 else hist_a
+                back = (k + 1) if actor_only else (k // 2 + 1)
+                src = hist_a if actor_only else (hist_c if k % 2 == 0 else hist_a)
                 out.append(src[t - back + D] if t - back >= 0 else zeros_hist)
             return out
 
@@ -596,13 +692,15 @@ class MAPPO:
             # the episode on its own stream (observe -> policy step || A* replan -> env step).  One group's small kernels and the
             # long tail of its replanning (the slowest of its searches gates its env step) then overlap with the other groups'
             # policy kernels instead of idling the GPU.  Same results for any G (the sampling RNG is keyed by the global row).
-            if pipelines is None:
-                pipelines = max(1, min(8, (B * N) // 8192)) if (timers is None and groups == 1) else 1
+            auto = pipelines is None
+            if auto:
+                pipelines = self.default_pipelines(B, N) if (timers is None and groups == 1) else 1
                 if os.environ.get("MARL_PIPELINES") and timers is None and groups == 1:      # tuning knob for tools/
                     pipelines = int(os.environ["MARL_PIPELINES"])
-            if pipelines > 1 and timers is None and groups == 1:
+            if pipelines > 1 and (timers is None or not auto) and groups == 1 and not actor_only:
+                # (an explicit pipelines=G together with timers: CUDA events around every launch of the pipelined schedule itself)
                 self._rollout_pipelined(engine, arena, T, seed, deterministic, int(pipelines), fused, oxy_i, o_count, hist_a, hist_c,
-                                        act, logp, v, zeros_hist)
+                                        act, logp, v, zeros_hist, timers=timers)
                 return self._train_batch(engine, arena, T, oxy, hist_a, hist_c, v, logp)
             # Single pipeline.  The A* replanning due every `difficulty` steps only needs the env state, not the action: it runs
             # on a side stream concurrently with the policy kernel and is joined before the env kernel consumes the paths.
@@ -625,11 +723,14 @@ class MAPPO:
                 timed("env_observe_kernel", engine.observe)
                 h_t = none_if_zero(history(t))
                 timed("policy_step_kernel", lambda: fused.step(engine, oxy_i, o_count, t, seed, deterministic, h_t, h_t,
-                                                               hist_a[t + D], hist_c[t + D], ha, hc, act[t], logp[t], v[t]))
+                                                               hist_a[t + D], hist_c[t + D], ha, hc, act[t], logp[t], v[t],
+                                                               nets=("actor",) if actor_only else ("actor", "critic")))
                 if join is not None:
                     main.wait_event(join)
                 engine.rollout_closed(arena, 1, t0=t, action_tape=act[t:t + 1], env_t0=t, groups=groups, timers=timers,
                                       skip_replan=join is not None)
+            if actor_only:
+                return self._train_batch(engine, arena, T, oxy, hist_a, hist_c, v, logp)
             engine.observe()
             h_fin = none_if_zero([hist_c[T - 1 + D]] + history(T - 1)[:D - 1])
             scratch = torch.empty(B, N, E, **f32)
@@ -643,12 +744,20 @@ class MAPPO:
                                    o_count, engine.p_adj_bits, engine.e_adj, engine.o_adj_bits)
             emb_a = enc.encode(graph, False, history(t))
             feat_a, ha = self.actor.features(emb_a.view(1, B * N, E), ha)
-            emb_c, feat_c = critic_step(t, graph)
-            a_i, _, lp, val = ops.act_head(feat_a[0], feat_c, self.actor.Mean.weight, self.actor.Mean.bias, w_eff,
-                                           self.critic.Mean.bias, seed, t, deterministic)
-            hist_a[t + D], hist_c[t + D] = emb_a, emb_c
-            v[t], logp[t], act[t] = val.view(B, N), lp.view(B, N), a_i.view(B, N)
+            if actor_only:
+                a_i, _, lp, _ = ops.act_head(feat_a[0], None, self.actor.Mean.weight, self.actor.Mean.bias, None, None, seed, t,
+                                             deterministic)
+                hist_a[t + D] = emb_a
+            else:
+                emb_c, feat_c = critic_step(t, graph)
+                a_i, _, lp, val = ops.act_head(feat_a[0], feat_c, self.actor.Mean.weight, self.actor.Mean.bias, w_eff,
+                                               self.critic.Mean.bias, seed, t, deterministic)
+                hist_a[t + D], hist_c[t + D] = emb_a, emb_c
+                v[t] = val.view(B, N)
+            logp[t], act[t] = lp.view(B, N), a_i.view(B, N)
             engine.rollout_closed(arena, 1, t0=t, action_tape=act[t:t + 1], env_t0=t, groups=groups)
+        if actor_only:
+            return self._train_batch(engine, arena, T, oxy, hist_a, hist_c, v, logp)
         # bootstrap value of the final state (:806-825): only the critic's dataset is updated once more
         engine.observe()
         graph = ops.GraphBatch(engine.p_state.to(torch.float32), engine.e_state.to(torch.float32), oxy, engine.map_id,
@@ -660,9 +769,21 @@ class MAPPO:
         v[T] = torch.nn.functional.linear(feat_c[0], w, self.critic.Mean.bias).view(B, N)
         return self._train_batch(engine, arena, T, oxy, hist_a, hist_c, v, logp)
 
+    @staticmethod
+    def default_pipelines(B, N):
+        """Env-group pipelines of a batched rollout: one per 8192 (env, agent) rows, at most 8."""
+        return max(1, min(8, (B * N) // 8192))
+
     def _rollout_pipelined(self, engine, arena, T, seed, deterministic, G, fused, oxy_i, o_count, hist_a, hist_c, act, logp, v,
-                           zeros_hist):
-        """G independent env-group pipelines, one stream (+ one A* side stream) each; see rollout_batched."""
+                           zeros_hist, timers=None):
+        """G independent env-group pipelines, one stream (+ one A* side stream) each; see rollout_batched.
+        timers: dict name -> list of (start, end) CUDA events recorded on the launching stream around every launch.  If it holds a
+        "_policy_dbg" int64 tensor [T, G, >= CTAs per launch, 16], every policy launch instead writes its per-CTA record there (slots
+        13 / 14 = %globaltimer at CTA start / end in ns, 15 = SM id; csrc/policy_fused.cu) - usable under CUDA-graph capture, which
+        is how bench.py times the kernel inside the schedule it reports."""
+        dbg = timers.pop("_policy_dbg", None) if timers is not None else None
+        if timers is not None and not timers and dbg is not None:
+            timers = None                                   # only the in-kernel records were asked for: no events (graph capture)
         B, N, E, D, L = engine.B, engine.N, self.embedding_dim, self.depth, self.num_layers
         dev = self.device
         main = torch.cuda.current_stream()
@@ -671,8 +792,19 @@ class MAPPO:
         rec_ptrs = arena.record_pointers()
         diff = int(engine.params.difficulty)
         full_tile = (128 // N) * N if N <= 128 else 0      # concurrent launches: full tiles, SMs left over for the neighbours
-        fork = torch.cuda.Event()
+        fork = torch.cuda.Event(enable_timing=timers is not None)
         fork.record(main)
+        if timers is not None:
+            timers["_t0"] = fork
+
+        def timed(name, stream, fn):
+            if timers is None:
+                return fn()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(stream)
+            fn()
+            b_.record(stream)
+            timers.setdefault(name, []).append((a_, b_))
 
         class _View:                                     # what FusedRolloutStep.step reads from an engine, for envs [lo, hi)
             pass
@@ -707,16 +839,18 @@ class MAPPO:
                         ev = torch.cuda.Event()
                         ev.record(st)
                         side.wait_event(ev)
-                        engine.evader_replan(lo, hi, side)
+                        timed("evader_kernel", side, lambda: engine.evader_replan(lo, hi, side))
                         join = torch.cuda.Event()
                         join.record(side)
-                    engine.observe(lo=lo, hi=hi)
+                    timed("env_observe_kernel", st, lambda: engine.observe(lo=lo, hi=hi))
                     h_t = hist_of(t)
-                    fused.step(view, oxy_i, o_count, t, seed, deterministic, h_t, h_t, hist_a[t + D][sl], hist_c[t + D][sl], ha, hc,
-                               act[t][sl], logp[t][sl], v[t][sl], row_offset=lo * N, tile_rows=full_tile)
+                    timed("policy_step_kernel", st, lambda: fused.step(
+                        view, oxy_i, o_count, t, seed, deterministic, h_t, h_t, hist_a[t + D][sl], hist_c[t + D][sl], ha, hc,
+                        act[t][sl], logp[t][sl], v[t][sl], row_offset=lo * N, tile_rows=full_tile,
+                        debug=dbg[t, g] if dbg is not None else None))
                     if join is not None:
                         st.wait_event(join)
-                    engine._closed_chunk(arena, rec_ptrs, lo, hi, t, 1, act[t:t + 1], 0, seed, st)
+                    timed("rollout_kernel", st, lambda: engine._closed_chunk(arena, rec_ptrs, lo, hi, t, 1, act[t:t + 1], 0, seed, st))
                 engine.observe(lo=lo, hi=hi)
                 h_fin = [hist_c[T - 1 + D][sl]] + hist_of(T - 1)[:D - 1]
                 scratch = torch.empty(hi - lo, N, E, dtype=torch.float32, device=dev)
@@ -725,6 +859,34 @@ class MAPPO:
                 done = torch.cuda.Event()
                 done.record(st)
             main.wait_event(done)
+
+    def explore_batched(self, engine, arena, T=None, seed=0, host_state=None, host_out=None, reset_reward_norm=False):
+        """The batched counterpart of `explore_env` (:731-740) - the call a user makes once per training iteration: one whole
+        episode of ALL envs of `engine` with both networks in the loop, replayed from a CUDA graph that is captured on the first
+        call (per engine / arena / T / seed; the weight images are re-packed inside the graph, so it follows the optimizer).
+
+        host_state: optional dict of HOST tensors (pinned for asynchronous copies) - `p_state` f64 [B,N,4], `e_state` f64 [B,4],
+        `target` i32 [B,2] - copied to the device before the episode (`BatchedPursuitEnv.load_host_state`, which also clears the
+        episode bookkeeping; `reset_reward_norm` additionally restarts the running reward statistics).
+        host_out: optional dict of HOST tensors filled after the episode - `episode_reward` i64 [B] (sum of the raw rewards over
+        pursuers and steps, the evaluator's return), `collision` u8 [B]; the call then synchronises the stream.
+        Returns the TrainBatch of the episode (device resident, ready for `train`)."""
+        T = T or arena.T
+        key = (id(engine), id(arena), int(T), int(seed))
+        graphs = self.__dict__.setdefault("_episode_graphs", {})
+        if key not in graphs:
+            graphs[key] = RolloutGraph(self, engine, arena, T, seed)
+        g = graphs[key]
+        if host_state is not None:
+            engine.load_host_state(reset_reward_norm=reset_reward_norm, **host_state)
+        g.replay()
+        if host_out is not None:
+            if "episode_reward" in host_out:
+                host_out["episode_reward"].copy_(arena.raw_reward[:T].sum(dim=(0, 2), dtype=torch.int64), non_blocking=True)
+            if "collision" in host_out:
+                host_out["collision"].copy_(engine.collision, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return g.batch
 
     def _train_batch(self, engine, arena, T, oxy, hist_a, hist_c, v, logp):
         B, D, dev = engine.B, self.depth, self.device

@@ -10,9 +10,10 @@ from . import _lib
 
 
 class RunningMeanStd:
-    def __init__(self, shape, device="cuda:0"):
+    def __init__(self, shape, device=None):
         self.shape = int(shape)
-        self.device = torch.device(device)
+        # default: the CURRENT device (one process per GPU: rank k must not allocate, or launch, on cuda:0)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._n = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._mean = torch.zeros(1, self.shape, dtype=torch.float64, device=self.device)
         self._S = torch.zeros_like(self._mean)
@@ -28,9 +29,14 @@ class RunningMeanStd:
         self._run(x, True)
 
     def _run(self, x, update):
-        x = torch.as_tensor(np.asarray(x).astype(np.int32).reshape(1, self.shape), device=self.device)
-        if not np.array_equal(np.asarray(x.cpu()), np.asarray(x.cpu()).astype(np.int64)):
+        a = np.asarray(x, dtype=np.float64)
+        if not np.array_equal(a, np.rint(a)):             # checked BEFORE the cast: a non-integer reward must not be truncated silently
             raise _lib.MarlError("Normalization: rewards of this env are integers")
+        x = torch.as_tensor(a.astype(np.int32).reshape(1, self.shape), device=self.device)
+        with torch.cuda.device(self.device):
+            return self._launch(x, update)
+
+    def _launch(self, x, update):
         _lib.check(_lib.lib().marl_welford_update(1, self.shape, _lib.ptr(x), _lib.ptr(self._n), _lib.ptr(self._mean),
                                                   _lib.ptr(self._S), _lib.ptr(self._std), _lib.ptr(self._out),
                                                   1 if update else 0, _lib.stream_ptr()), "marl_welford_update")
@@ -38,7 +44,7 @@ class RunningMeanStd:
 
 
 class Normalization:
-    def __init__(self, shape, device="cuda:0"):
+    def __init__(self, shape, device=None):
         self.running_ms = RunningMeanStd(shape=shape, device=device)
 
     def __call__(self, x, update=True):
@@ -67,7 +73,7 @@ class Normalization:
 class RewardScaling:
     """DHGN/normalization.py:38-52 (unused by the reference's training loop; kept for API completeness)."""
 
-    def __init__(self, shape, gamma, device="cuda:0"):
+    def __init__(self, shape, gamma, device=None):
         self.shape, self.gamma = shape, gamma
         self.running_ms = RunningMeanStd(shape=shape, device=device)
         self.R = np.zeros(self.shape)

@@ -115,6 +115,22 @@ class BatchedPursuitEnv:
         if time_step is not None:
             self.time_step.fill_(int(time_step))
 
+    def load_host_state(self, p_state=None, e_state=None, target=None, reset_reward_norm=False):
+        """Start-of-episode state from HOST tensors (pinned memory makes the copies asynchronous): p_state f64 [B,N,4], e_state f64
+        [B,4], target i32 [B,2]; clears the episode bookkeeping (time step, flags, evader path, target-tape cursor) and, on request,
+        the running reward statistics.  Everything is queued on the current stream - no synchronisation."""
+        for name, src in (("p_state", p_state), ("e_state", e_state), ("target", target)):
+            if src is not None:
+                dst = getattr(self, name)
+                if src.dtype != dst.dtype or src.numel() != dst.numel():
+                    raise _lib.MarlError(f"load_host_state: {name} must be {dst.dtype} with {dst.numel()} elements")
+                dst.copy_(src.view(dst.shape), non_blocking=True)
+        self.start_episode()
+        self.tape_pos.zero_()
+        if reset_reward_norm:
+            for t in (self.wf_n, self.wf_mean, self.wf_S, self.wf_std):
+                t.zero_()
+
     def set_target_tape(self, tape):
         """tape: int [B,L,2] candidate targets consumed by mid-episode init_target (base_env.py:52-70)."""
         tape = np.asarray(tape, dtype=np.int32).reshape(self.B, -1, 2)

@@ -82,3 +82,64 @@ def test_evaluator_bookkeeping_and_batched_episodes():
     ev.max_r = row[1] + 1e9                                                              # a worse average is not saved
     _, saved2 = ev.run(aw, cw, 2000, 0.0, (0.0, 0.0))
     assert saved2 == [] and len(ev.recorder) == 2 and ev.total_step == 2000
+
+
+@pytest.mark.parametrize("n_def,depth,T", [(8, 1, 20), (5, 3, 16)])
+def test_batched_evaluator_episode_equals_evaluate(n_def, depth, T):
+    """The Evaluator's batched arg-max episodes (`rollout_batched(deterministic=True, actor_only=True)`) are the reference's
+    `evaluate()` episodes (evaluator.py:118-156): the actor alone, conditioned on its OWN previous embeddings A(t-1), A(t-2), ...
+    (not on the training rollout's aliased actor / critic history).  One env, same initial state: same action at every step, same
+    rewards, same return, bit-identical final pursuer state - for depth 1 and 3, where the two histories differ from t = 1 on."""
+    from distributed_multi_agent_reinforcement_learning_b200.evaluator import evaluate
+    from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
+    from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import Pursuit_Env, RolloutArena
+    cfg = _cfg(n_def, depth, T, 128)
+    torch.manual_seed(11)
+    agent = MAPPO(cfg, None, None, "Evaluator")
+    with torch.no_grad():                                    # biases are zero-initialised: make them matter
+        for p in agent.ac_parameters:
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+    env = Pursuit_Env(cfg)
+
+    def seed_all():
+        random.seed(77)
+        np.random.seed(77)
+
+    seed_all()
+    actions, rewards = [], []
+    orig_step = env.step
+
+    def step(a):
+        actions.append(np.asarray(a).astype(np.int32).copy())
+        out = orig_step(a)
+        rewards.append(np.asarray(out[0], dtype=np.int32).copy())
+        return out
+    env.step = step
+    ret = evaluate(env, agent.actor, cfg)
+    p_final = np.asarray(env.get_state("defender"), np.float64)
+    env.step = orig_step
+    # the same episode as ONE batched rollout on the facade's engine
+    seed_all()
+    env.reset()
+    env.begin_batched_episode()
+    eng = env.engine
+    arena = RolloutArena(eng.params, 1, T, eng.device)
+    for fused in (True, False):
+        snap = eng.snapshot()
+        agent.rollout_batched(eng, arena, T, seed=0, deterministic=True, actor_only=True, use_fused=fused)
+        torch.cuda.synchronize()
+        got_a = arena.a_n[:T, 0].cpu().numpy().astype(np.int32)
+        same = (got_a == np.stack(actions)).all(axis=1)
+        assert same.all(), f"fused={fused}: first differing step {int(np.argmin(same))}"
+        assert np.array_equal(arena.raw_reward[:T, 0].cpu().numpy(), np.stack(rewards))
+        assert int(arena.raw_reward[:T].sum()) == int(ret[0]) and ret[1] == T - 1
+        assert np.array_equal(eng.p_state[0].cpu().numpy().view(np.int64), p_final.view(np.int64))
+        eng.restore(snap)
+    # and the aliased training history gives a DIFFERENT actor input from t = 1 on (what the evaluator must not use)
+    tb_eval = agent.rollout_batched(eng, arena, T, seed=0, deterministic=True, actor_only=True)
+    emb_eval = tb_eval.hist_a.clone()
+    eng.restore(snap)
+    tb_train = agent.rollout_batched(eng, arena, T, seed=0, deterministic=True)
+    assert torch.equal(emb_eval[depth], tb_train.hist_a[depth])                      # t = 0: no history yet
+    assert not torch.allclose(emb_eval[depth + 1], tb_train.hist_a[depth + 1], rtol=1e-4, atol=1e-5)

@@ -178,10 +178,13 @@ def test_rollout_forward_reproduces_reference_buffer(path):
                 val = torch.nn.functional.linear(fc[0], w_eff, m.critic.Mean.bias)[:, 0]
                 logp_all = torch.log_softmax(torch.nn.functional.linear(fa[0], m.actor.Mean.weight, m.actor.Mean.bias), -1)
                 lp = logp_all.gather(-1, buf["a_n"][b, t].long().unsqueeze(-1))[:, 0]
-                torch.testing.assert_close(emb_a[0], hist_a[t + D], rtol=1e-5, atol=2e-6)
-                torch.testing.assert_close(emb_c[0], hist_c[t + D], rtol=1e-5, atol=2e-6)
-                torch.testing.assert_close(val, buf["v_n"][b, t], rtol=1e-5, atol=2e-6)
-                torch.testing.assert_close(lp, buf["a_logprob_n"][b, t], rtol=1e-5, atol=2e-6)
+                # 1e-5 relative; the absolute floor is 1e-5 of the activations' scale (embeddings of the 128-wide networks reach
+                # ~0.5: an element that cancels to 0.03 still carries the rounding of its O(1) summands)
+                tol = dict(rtol=1e-5, atol=2e-6 if emb == 32 else 5e-6)
+                torch.testing.assert_close(emb_a[0], hist_a[t + D], **tol)
+                torch.testing.assert_close(emb_c[0], hist_c[t + D], **tol)
+                torch.testing.assert_close(val, buf["v_n"][b, t], **tol)
+                torch.testing.assert_close(lp, buf["a_logprob_n"][b, t], **tol)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -494,3 +497,54 @@ def test_checkpoint_file_set_round_trip(tmp_path):
     # pickled whole module, as evaluator.py:329-330 consumes it
     sd = torch.load(os.path.join(tmp_path, "actor.pth"), weights_only=False).state_dict()
     assert list(sd.keys()) == list(a.actor.state_dict().keys())
+
+
+def _train_grads(m, buf, total_steps, **kw):
+    trace = {}
+    m.train(_Big(buf), total_steps, return_numpy=False, trace=trace, **kw)
+    return m.ac_optimizer.flat_grad.clone(), trace
+
+
+def test_shuffled_minibatches_through_the_gather_kernel():
+    """algo.shuffle_minibatches / train(permutation=...) (north star part 4; the reference is sequential, :665, so the default is
+    off): with the identity permutation the gathered epoch equals the sequential epoch bit for bit, and with a random permutation
+    it equals the sequential epoch on the correspondingly permuted buffer."""
+    from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
+    path = os.path.join(GOLDEN_DIR, "algo_d1_n8_e128.npz")
+    fx, depth, n_def, T, episodes, mb, seed, emb = _load(path)
+    m = MAPPO(_cfg(depth, n_def, T, emb), episodes, mb, "Learner")
+    _load_weights(m, fx)
+    u0, v0 = m.critic.Mean.weight_u.clone(), m.critic.Mean.weight_v.clone()
+
+    def reset_sn():          # the power-iteration buffers advance on every critic forward: same start for every run
+        m.critic.Mean.weight_u.copy_(u0)
+        m.critic.Mean.weight_v.copy_(v0)
+    buf = {k[4:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("buf.")}
+    steps = int(fx["total_steps"])
+    # the gathered minibatch IS the sliced minibatch, tensor for tensor, bit for bit
+    from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import TrainBatch
+    tb = TrainBatch.from_reference({k: v.cuda() for k, v in buf.items()}, depth)
+    sliced = tb.minibatch(1, 4)
+    gathered, _ = tb.minibatch_indexed(torch.arange(1, 4, device="cuda"))
+    for key in TrainBatch.KEYS + ("oxy", "o_count_train"):
+        assert torch.equal(getattr(sliced, key), getattr(gathered, key)), key
+    g_seq, tr_seq = _train_grads(m, buf, steps)
+    reset_sn()
+    g_id, tr = _train_grads(m, buf, steps, permutation=list(range(episodes)))
+    assert torch.equal(tr["permutation"].cpu(), torch.arange(episodes))
+    for a_, b_ in zip(tr_seq["mb"], tr["mb"]):            # identity permutation: the forward passes are bit-identical ...
+        assert torch.equal(a_["logp"], b_["logp"]) and torch.equal(a_["ent"], b_["ent"]) and torch.equal(a_["val"], b_["val"])
+    # ... and so are the gradients up to the summation order of the message layers' atomic weight-gradient reduction
+    torch.testing.assert_close(g_id, g_seq, rtol=1e-5, atol=1e-7)
+    perm = [3, 0, 4, 2, 1]
+    reset_sn()
+    g_perm, _ = _train_grads(m, buf, steps, permutation=perm)
+    reset_sn()
+    g_ref, _ = _train_grads(m, {k: v[perm] for k, v in buf.items()}, steps)
+    # (the advantage statistics are summed in a different env order in the two runs: equal up to fp64 rounding of the mean / std)
+    torch.testing.assert_close(g_perm, g_ref, rtol=1e-5, atol=1e-7)
+    assert not torch.allclose(g_perm, g_seq, rtol=1e-3, atol=1e-6)
+    # the config switch draws a seeded device permutation
+    reset_sn()
+    _, tr2 = _train_grads(m, buf, steps, shuffle=True, shuffle_seed=11)
+    assert sorted(tr2["permutation"].cpu().tolist()) == list(range(episodes))

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--steps", type=int, default=150)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--depth", type=int, default=1)
+    ap.add_argument("--allreduce", default=None, choices=[None, "update", "minibatch"],
+                    help="gradient exchange: once per update (reference, default) or once per PPO minibatch")
     ap.add_argument("--host-reset", action="store_true", help="generate episodes on the host with the reference's generators (slow)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -58,15 +60,18 @@ def main():
             env.reset_device(seed=1000 * rank + it)            # same rules, generated on the GPU (csrc/reset_kernels.cu)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        tb = mappo.rollout_batched(env, arena, T, seed=it)
+        if not args.host_reset:
+            assert int(env.reset_fail.sum()) == 0, "device reset could not place every pursuer / evader"
+        tb = mappo.rollout_batched(env, arena, T, seed=it * world + rank)     # distinct sampling streams per replica and iteration
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         assert int(env.evader_status.max()) == 0, "evader search overflow / target tape exhausted"
         ep_reward = float(arena.raw_reward.sum(dim=(0, 2)).float().mean())
         collided = float(env.collision.float().mean())
         total_steps += world * B * T
-        obj_c, obj_a, _, _ = mappo.train(tb, total_steps, return_numpy=False)
-        mappo.update(total_steps)
+        for _ in range(int(cfg.algo.epochs)):                       # main.py:99: K epochs over the same buffers, one Adam step each
+            obj_c, obj_a, _, _ = mappo.train(tb, total_steps, return_numpy=False, allreduce=args.allreduce)
+            mappo.update(total_steps)
         torch.cuda.synchronize()
         t3 = time.perf_counter()
         stats = torch.tensor([ep_reward, collided, obj_c, obj_a], device=dev, dtype=torch.float64)
