@@ -1289,6 +1289,312 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
     if (warp == WW + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(M::TMEM_COLS) : "memory");
 }
 
+
+// =================================================================================================================================
+// PAIR kernel: ONE CTA runs the actor chain AND the critic chain of the same 128-row tile, interleaved step by step.
+//
+// The unit chain of one network is a dependence chain: SIMT phase -> MMA group -> epilogue -> MMA group -> ...  With one chain per
+// CTA the 16 worker warps idle while the tensor pipe runs (~30 % of an item) and the tensor pipe idles while they work.
+// Here the workers alternate between the two chains: they finish a step of the actor chain, hand its tile to the issuer, and do
+// the same step of the critic chain while the actor's MMAs run, and vice versa - the same 16 warps at 8 rows each (the code
+// that fits 96 registers), so unlike two co-resident CTAs nothing is paid in registers or shared memory per warp.
+//   shared memory : X_actor 64 KB + X_critic 64 KB + weight ring 2 x 32 KB + boundary-cell staging 32 KB + 3 KB   (227 KB)
+//   tensor memory : 256 columns per chain.  The encoder needs two 128-column accumulators; the GRU runs in two 64-column halves
+//                   (r @0, z @64, n_i @128, n_h @192) with x and h_prev re-staged in X for each half (they come back from L2),
+//                   the new state written straight from registers to the OUTPUT hidden buffer (the caller ping-pongs).
+//   both chains share the fp32 copy of the tile's states and the staged boundary cells; each has its own pair of mbarriers.
+// The loader and the issuer walk the two unit programs group by group in the same order as the workers: A.g0, C.g0, A.g1, ...
+struct MemPair {
+    static constexpr int NST = 2, STAGE = WSTAGE;
+    static constexpr int XC_OFF = X_BYTES, RING_OFF = 2 * X_BYTES, MISC_OFF = RING_OFF + NST * STAGE, OXY_OFF = MISC_OFF + MISC_BYTES;
+    static constexpr int BYTES = OXY_OFF + OXY_BYTES;
+    static constexpr int BAR_READY = 2 * NST, BAR_DONE = 2 * NST + 2;      // [chain]
+};
+static_assert(MemPair::BYTES <= 232448, "PAIR kernel shared memory");
+
+// one 64-column half of the GRU cell for WW worker warps: thread <-> row 32*(warp&3)+lane, columns [CPH*(warp>>2), +CPH) of the half
+template <int WW>
+__device__ void epi_cell_half_w(const Ctx &c, int l, int half, bool want_value, float *s_part)
+{
+    constexpr int CG = WW / 4, CPH = 64 / CG;
+    const NetArgs *na = c.na;
+    const int row = 32 * (c.warp & 3) + c.lane, hh = c.warp >> 2;
+    const float *bi = na->b_ih[l], *bh = na->b_hh[l];
+    const uint32_t taddr = c.tmem + ((uint32_t)(32 * (c.warp & 3)) << 16);
+    int64_t gr;
+    int env, i;
+    const bool ok = row_info(c, row, gr, env, i);
+    float *dst = na->hidden_out + ((int64_t)l * c.a->R + gr) * E;
+    float vdot = 0.f;
+#pragma unroll 1
+    for (int j0 = CPH * hh; j0 < CPH * hh + CPH; j0 += 8) {
+        uint32_t ar[8], az[8], an[8], ahn[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(ar[0]), "=r"(ar[1]), "=r"(ar[2]), "=r"(ar[3]), "=r"(ar[4]), "=r"(ar[5]), "=r"(ar[6]), "=r"(ar[7]) : "r"(taddr + (uint32_t)j0));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(az[0]), "=r"(az[1]), "=r"(az[2]), "=r"(az[3]), "=r"(az[4]), "=r"(az[5]), "=r"(az[6]), "=r"(az[7]) : "r"(taddr + (uint32_t)(64 + j0)));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(an[0]), "=r"(an[1]), "=r"(an[2]), "=r"(an[3]), "=r"(an[4]), "=r"(an[5]), "=r"(an[6]), "=r"(an[7]) : "r"(taddr + (uint32_t)(128 + j0)));
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(ahn[0]), "=r"(ahn[1]), "=r"(ahn[2]), "=r"(ahn[3]), "=r"(ahn[4]), "=r"(ahn[5]), "=r"(ahn[6]), "=r"(ahn[7]) : "r"(taddr + (uint32_t)(192 + j0)));
+        const int col = 64 * half + j0;
+        float hp[8];
+        x_load8(c.X, row, col >> 3, hp);
+        tmem_wait_ld();
+        float hn[8];
+#pragma unroll
+        for (int q4 = 0; q4 < 8; q4 += 4) {
+            const float4 bir = __ldg(reinterpret_cast<const float4 *>(bi + col + q4)), bhr = __ldg(reinterpret_cast<const float4 *>(bh + col + q4));
+            const float4 biz = __ldg(reinterpret_cast<const float4 *>(bi + E + col + q4)), bhz = __ldg(reinterpret_cast<const float4 *>(bh + E + col + q4));
+            const float4 bin = __ldg(reinterpret_cast<const float4 *>(bi + 2 * E + col + q4)), bhn = __ldg(reinterpret_cast<const float4 *>(bh + 2 * E + col + q4));
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (want_value) wv = __ldg(reinterpret_cast<const float4 *>(na->head_w_eff + col + q4));
+            const float f_bir[4] = {bir.x, bir.y, bir.z, bir.w}, f_bhr[4] = {bhr.x, bhr.y, bhr.z, bhr.w};
+            const float f_biz[4] = {biz.x, biz.y, biz.z, biz.w}, f_bhz[4] = {bhz.x, bhz.y, bhz.z, bhz.w};
+            const float f_bin[4] = {bin.x, bin.y, bin.z, bin.w}, f_bhn[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
+            const float f_w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float r = fast_sigmoid((__uint_as_float(ar[q4 + q]) + f_bir[q]) + f_bhr[q]);
+                const float z = fast_sigmoid((__uint_as_float(az[q4 + q]) + f_biz[q]) + f_bhz[q]);
+                const float n = fast_tanh((__uint_as_float(an[q4 + q]) + f_bin[q]) + r * (__uint_as_float(ahn[q4 + q]) + f_bhn[q]));
+                hn[q4 + q] = (1.f - z) * n + z * hp[q4 + q];
+                vdot = fmaf(f_w[q], hn[q4 + q], vdot);
+            }
+        }
+        if (ok) {
+            *reinterpret_cast<float4 *>(dst + col) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4 *>(dst + col + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        }
+    }
+    if (want_value) s_part[(half * CG + hh) * ROWS + row] = vdot;
+}
+
+template <int WW>
+__global__ void __launch_bounds__(Lay<WW>::THREADS, 1)
+policy_pair_kernel(const __grid_constant__ StepArgs a)
+{
+    using M = MemPair;
+    constexpr int NST = M::NST;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    unsigned char *Wst = smem + M::RING_OFF;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + M::MISC_OFF);   // full[2], empty[2], a_ready[2 chains], mma_done[2 chains]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 4);
+    float4 *s_p = reinterpret_cast<float4 *>(bars + 16);
+    float4 *s_e = s_p + ROWS;
+    float2 *s_oxy = reinterpret_cast<float2 *>(smem + M::OXY_OFF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[NST + s]), 1);
+        }
+        for (int ch = 0; ch < 2; ++ch) {
+            mbar_init(smem_u32(&bars[M::BAR_READY + ch]), Lay<WW>::WORKERS);
+            mbar_init(smem_u32(&bars[M::BAR_DONE + ch]), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == WW + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < WW) {
+        // ================================================================================= workers
+        Ctx c;
+        c.a = &a; c.row0 = (int64_t)tile * a.rows_per_tile; c.warp = warp; c.lane = lane; c.group = 0; c.s_p = s_p; c.s_e = s_e;
+        c.s_val = reinterpret_cast<float *>(s_oxy);      // value partials: the boundary-cell staging is dead once the GRU starts
+        c.s_oxy = s_oxy; c.oxy_cap = OXY_CAP; c.wait_sleep_ns = 0u;
+        c.na = &a.net[0]; c.X = smem; c.tmem = tmem_base; c.bar_a_ready = 0; c.bar_mma_done = 0;
+        {
+            const int t = threadIdx.x;
+            if (t < ROWS) {
+                int64_t gr;
+                int env, i;
+                s_p[t] = row_info(c, t, gr, env, i) ? load_p(&a, gr) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else if (t < ROWS + 32) {
+                const int64_t env = c.row0 / a.N + (t - ROWS);
+                s_e[t - ROWS] = (ROWS / a.N <= 32 && t - ROWS < ROWS / a.N && env < a.B) ? load_e(&a, (int)env) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            worker_sync<WW>();
+        }
+        long long tk[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) tk[q] = 0;
+        long long t_prev = clock64();
+        const long long t_begin = t_prev;
+        if (a.dbg && threadIdx.x == 0) {
+            unsigned long long gt;
+            unsigned smid;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            tk[13] = (long long)gt;
+            tk[15] = (long long)smid;
+        }
+        const int D = a.depth, G0 = 7 + 3 * D, S_ACTOR = G0 + 9, S_CRITIC = G0 + 8;
+#pragma unroll 1
+        for (int s = 0; s < S_ACTOR; ++s) {
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                if (s >= (ch == 0 ? S_ACTOR : S_CRITIC)) continue;
+                const NetArgs *na = &a.net[ch];
+                c.na = na;
+                c.X = smem + ch * M::XC_OFF;
+                c.tmem = tmem_base + 256u * (uint32_t)ch;
+                c.bar_a_ready = smem_u32(&bars[M::BAR_READY + ch]);
+                c.bar_mma_done = smem_u32(&bars[M::BAR_DONE + ch]);
+                if (s > 0) {                                   // the chain's previous MMA group: accumulators ready, X free again
+                    mbar_wait(c.bar_mma_done, (uint32_t)((s - 1) & 1));
+                    tc_fence_after();
+                }
+                PF_TICK(11);
+                bool signal = true;
+                if (s < 6) {
+                    if ((s & 1) == 0) { phase_msg<WW>(c, s >> 1); PF_TICK(0); }                          // messages of relation s/2 -> X
+                    else { epi_store<WW>(c, 0, na->b_av, true, nullptr, 0, nullptr); PF_TICK(1); }      // AGG_vertex_0 output -> X
+                } else if (s == 6) {
+                    epi_store<WW>(c, 128, na->b_sem, false, na->sem_w, na->sem_ld, nullptr);             // h0 (no activation)
+                    PF_TICK(1);
+                } else if (s < G0) {
+                    const int k = (s - 7) / 3, sub = (s - 7) % 3;
+                    if (sub == 0) {
+                        float4 pre[Lay<WW>::RPW];
+                        uint32_t words[4] = {0u, 0u, 0u, 0u};
+                        phase_fcra_prefetch<WW>(c, k, pre, words);
+                        phase_fcra_finish<WW>(c, k, pre, words);
+                        PF_TICK(2);
+                    } else if (sub == 1) {
+                        epi_store<WW>(c, 0, na->b_aggf[k], true, nullptr, 0, nullptr);
+                        PF_TICK(1);
+                    } else {
+                        epi_store<WW>(c, 128, na->b_f[k], true, nullptr, 0, k == D - 1 ? na->emb_out : nullptr);
+                        PF_TICK(1);
+                    }
+                } else if (s < G0 + 8) {
+                    const int l = (s - G0) >> 2, sub = (s - G0) & 3;
+                    const float *h_src = na->hidden_in + (int64_t)l * a.R * E;
+                    if ((sub & 1) == 0) {                      // W_ih group of this half done: X <- h_prev for the W_hh group
+                        fill_x<WW>(c, h_src);
+                        PF_TICK(3);
+                    } else {
+                        const int half = sub >> 1;
+                        const bool want_value = l == 1 && na->head_w_eff != nullptr;
+                        epi_cell_half_w<WW>(c, l, half, want_value, c.s_val);
+                        worker_sync<WW>();                     // every reader of h_prev in X is done; the half's new state is in memory
+                        PF_TICK(4);
+                        if (half == 0) {                       // X <- x again for the other half
+                            fill_x<WW>(c, l == 0 ? na->emb_out : na->hidden_out);
+                            PF_TICK(3);
+                        } else if (l == 0 || ch == 0) {        // X <- the layer's new state: input of layer 1 / of the actor head
+                            fill_x<WW>(c, na->hidden_out + (int64_t)l * a.R * E);
+                            PF_TICK(3);
+                        } else {                               // critic, last layer: the value
+                            signal = false;
+                            const int row = 32 * (warp & 3) + lane, hh = warp >> 2;
+                            int64_t gr;
+                            int env, i;
+                            if (want_value && hh == 0 && a.value && row_info(c, row, gr, env, i)) {
+                                float v = 0.f;
+#pragma unroll
+                                for (int q = 0; q < 2 * (WW / 4); ++q) v += c.s_val[q * ROWS + row];
+                                a.value[gr] = v + __ldg(na->head_b);
+                            }
+                        }
+                    }
+                } else {
+                    epi_head<MARL_NUM_ACTIONS>(c);
+                    PF_TICK(5);
+                    signal = false;
+                }
+                if (signal) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    tc_fence_before();
+                    mbar_arrive(c.bar_a_ready);
+                }
+            }
+        }
+        if (a.dbg && threadIdx.x == 0) {
+            tk[12] = clock64() - t_begin;
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+            tk[14] = (long long)gt;
+            for (int q = 0; q < 16; ++q) a.dbg[(size_t)blockIdx.x * 16 + q] = tk[q];
+        }
+    } else if (warp == WW) {
+        // ================================================================================= weight loader
+        if (lane == 0) {
+            int it = 0, iu[2] = {0, 0};
+            while (iu[0] < a.net[0].n_units || iu[1] < a.net[1].n_units) {
+                for (int ch = 0; ch < 2; ++ch) {
+                    const NetArgs *na = &a.net[ch];
+                    bool last = iu[ch] >= na->n_units;
+                    while (!last) {
+                        const Unit un = na->u[iu[ch]++];
+                        last = un.last != 0;
+                        const uint32_t bytes = 2u * un.n_out * 128u;
+                        for (int kb = 0; kb < NKB; ++kb, ++it) {
+                            const int st = it % NST, round = it / NST;
+                            if (round > 0) mbar_wait(smem_u32(&bars[NST + st]), (uint32_t)((round - 1) & 1));
+                            mbar_expect_tx(smem_u32(&bars[st]), bytes);
+                            bulk_g2s(smem_u32(Wst + st * M::STAGE), na->packed + un.off + (size_t)kb * bytes, bytes, smem_u32(&bars[st]));
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================================================================= MMA issuer
+        if (lane == 0) {
+            int it = 0, iu[2] = {0, 0}, grp[2] = {0, 0};
+            while (iu[0] < a.net[0].n_units || iu[1] < a.net[1].n_units) {
+                for (int ch = 0; ch < 2; ++ch) {
+                    const NetArgs *na = &a.net[ch];
+                    if (iu[ch] >= na->n_units) continue;
+                    mbar_wait(smem_u32(&bars[M::BAR_READY + ch]), (uint32_t)(grp[ch] & 1));
+                    tc_fence_after();
+                    const unsigned char *X = smem + ch * M::XC_OFF;
+                    bool last = false;
+                    while (!last) {
+                        const Unit un = na->u[iu[ch]++];
+                        last = un.last != 0;
+                        const uint32_t idesc = idesc_f16(un.n_out);
+                        const uint32_t acc = tmem_base + 256u * (uint32_t)ch + un.acc_col;
+                        const uint32_t lo_off = (uint32_t)un.n_out * 128u;
+                        for (int kb = 0; kb < NKB; ++kb, ++it) {
+                            const int st = it % NST, round = it / NST;
+                            mbar_wait(smem_u32(&bars[st]), (uint32_t)(round & 1));
+                            tc_fence_after();
+                            const uint32_t xa = smem_u32(X + kb * XKB), wb = smem_u32(Wst + st * M::STAGE);
+                            const uint64_t a_hi0 = make_desc(xa), a_lo0 = make_desc(xa + TILE), b_hi0 = make_desc(wb), b_lo0 = make_desc(wb + lo_off);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint64_t a_hi = a_hi0 + 2 * kk, a_lo = a_lo0 + 2 * kk, b_hi = b_hi0 + 2 * kk, b_lo = b_lo0 + 2 * kk;
+                                umma_f16(acc, a_hi, b_hi, idesc, (un.accumulate || kb || kk) ? 1u : 0u);
+                                umma_f16(acc, a_lo, b_hi, idesc, 1u);
+                                umma_f16(acc, a_hi, b_lo, idesc, 1u);
+                            }
+                            umma_commit(smem_u32(&bars[NST + st]));
+                        }
+                    }
+                    umma_commit(smem_u32(&bars[M::BAR_DONE + ch]));
+                    ++grp[ch];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WW + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
 // ---- weight packing: one unit = W[rows, k0 : k0+128] -> 2 k-blocks (K = 64) x (hi plane, lo plane) in the smem image ------------
 __global__ void __launch_bounds__(256)
 pack_unit_kernel(const float *__restrict__ W, int64_t ld, int rows_valid, int n_out, int k0, unsigned char *__restrict__ out)
@@ -1480,10 +1786,12 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
     // cells for the shared-memory staging of the env-grouped message path and envs of <= 16 agents-per-warp rows as usual
     const bool pingpong = (!has_a || (actor_io->d_hidden_out && actor_io->d_hidden_out != actor_io->d_hidden)) &&
                           (!has_c || (critic_io->d_hidden_out && critic_io->d_hidden_out != critic_io->d_hidden));
-    MARL_REQUIRE(s->variant >= 0 && s->variant <= 2, "marl_policy_rollout_step: variant=%d (0..2)", s->variant);
-    MARL_REQUIRE(s->variant != 2 || pingpong, "marl_policy_rollout_step: variant 2 needs d_hidden_out != d_hidden");
-    const bool dual = s->variant == 2 || (s->variant == 0 && pingpong && pf::kDualByDefault && s->O <= pf::Mem<true>::OXY);
-    a.rows_per_tile = pf::choose_rows_per_tile(a.R, s->N, nets, dual ? 2 : 1, s->tile_rows);
+    MARL_REQUIRE(s->variant >= 0 && s->variant <= 3, "marl_policy_rollout_step: variant=%d (0..3)", s->variant);
+    MARL_REQUIRE((s->variant != 2 && s->variant != 3) || pingpong, "marl_policy_rollout_step: variant %d needs d_hidden_out != d_hidden", s->variant);
+    MARL_REQUIRE(s->variant != 3 || (has_a && has_c), "marl_policy_rollout_step: variant 3 (actor + critic chains in one CTA) needs both networks");
+    const bool pair = s->variant == 3;
+    const bool dual = pair || s->variant == 2 || (s->variant == 0 && pingpong && pf::kDualByDefault && s->O <= pf::Mem<true>::OXY);
+    a.rows_per_tile = pf::choose_rows_per_tile(a.R, s->N, pair ? 1 : nets, (dual && !pair) ? 2 : 1, s->tile_rows);
     a.n_tiles = (int)((a.R + a.rows_per_tile - 1) / a.rows_per_tile);
     a.p_state = s->d_p_state; a.e_state = s->d_e_state; a.oxy = s->d_oxy; a.map_id = s->d_map_id; a.o_count = s->d_o_count;
     a.p_adj = s->d_p_adj_bits; a.e_adj = s->d_e_adj; a.o_adj = s->d_o_adj_bits;
@@ -1495,7 +1803,7 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
     if (has_c) { rc = fill_net(a.net[1], critic_w, critic_io, s->depth, 0, s->action_dim, dual); if (rc) return rc; }
     a.net_count = nets;
     a.net_first = has_a ? 0 : 1;
-    const unsigned grid = (unsigned)(a.n_tiles * a.net_count);
+    const unsigned grid = (unsigned)(a.n_tiles * (pair ? 1 : a.net_count));
     auto launch = [&](auto kernel, int threads, int smem_bytes, bool max_carveout) -> int {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e == cudaSuccess && max_carveout) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1504,7 +1812,8 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
         return MARL_OK;
     };
     // one CTA per SM: 16 worker warps unless the env-grouped message path needs a whole 16-agent env per warp
-    if (dual) rc = launch(pf::policy_step_kernel<8, true>, pf::Lay<8>::THREADS, pf::Mem<true>::BYTES, true);
+    if (pair) rc = launch(pf::policy_pair_kernel<16>, pf::Lay<16>::THREADS, pf::MemPair::BYTES, false);
+    else if (dual) rc = launch(pf::policy_step_kernel<8, true>, pf::Lay<8>::THREADS, pf::Mem<true>::BYTES, true);
     else if (!(s->N == 16 && s->O <= pf::OXY_CAP)) rc = launch(pf::policy_step_kernel<16, false>, pf::Lay<16>::THREADS, pf::Mem<false>::BYTES, false);
     else rc = launch(pf::policy_step_kernel<8, false>, pf::Lay<8>::THREADS, pf::Mem<false>::BYTES, false);
     if (rc) return rc;

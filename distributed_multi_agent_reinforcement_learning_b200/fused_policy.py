@@ -4,6 +4,7 @@ the heads of the actor AND the critic for all B envs of a step (DHGN/mappo_paral
 `FusedRolloutStep` owns the packed (hi/lo TF32, pre-swizzled) weight images and the ctypes structs; it is rebuilt (re-packed)
 whenever the weights change, i.e. once per rollout."""
 import ctypes as C
+import os
 
 import torch
 
@@ -30,6 +31,11 @@ class PolicyStep(C.Structure):
                [(n, C.c_void_p) for n in ("d_p_state", "d_e_state", "d_oxy", "d_map_id", "d_o_count", "d_p_adj_bits",
                                           "d_e_adj", "d_o_adj_bits", "d_action", "d_logp", "d_value", "d_debug")] + \
                [("row_offset", C.c_int64), ("tile_rows", C.c_int32), ("reserved", C.c_int32)]
+
+
+# Kernel variant used when the caller does not ask for one (marl_policy_step.variant): 3 = the actor and the critic chain of a row
+# tile interleaved in ONE CTA (policy_pair_kernel) whenever both networks are stepped, 1 = one (tile, network) item per CTA.
+DEFAULT_VARIANT = int(os.environ.get("MARL_POLICY_VARIANT", "3"))
 
 
 def supported(mappo):
@@ -93,9 +99,14 @@ class FusedRolloutStep:
              nets=("actor", "critic"), force_action=False, debug=None, variant=0, row_offset=0, tile_rows=0):
         """hist_*: list (k = 0 newest) of [B,N,E] tensors or None (zeros); emb_*: [B,N,E] outputs; ha/hc: [2,B*N,E] in/out;
         action i32 [B,N], logp / value f32 [B,N] outputs.
-        variant: 0 / 1 = one CTA per SM (the default; hidden state updated in place), 2 = two CTAs per SM: that kernel reads the
-        previous hidden state from one buffer and writes the new one to another; afterwards the two tensors trade their storage, so
-        for the caller `ha` / `hc` are still updated "in place" (views taken before the call keep the old state)."""
+        variant: 0 = DEFAULT_VARIANT, 1 = one (tile, network) item per CTA (hidden state updated in place), 2 = two such CTAs per
+        SM, 3 = both networks' chains of a tile interleaved in one CTA.  Variants 2 and 3 read the previous hidden state from one
+        buffer and write the new one to another; afterwards the two tensors trade their storage, so for the caller `ha` / `hc`
+        are still updated "in place" (views taken before the call keep the old state)."""
+        if int(variant) == 0 and DEFAULT_VARIANT == 3 and "actor" in nets and "critic" in nets and not (engine.N == 16 and engine.O <= 256):
+            variant = 3          # (16-agent envs keep the 8-worker-warp kernel: their message path needs a whole env per warp)
+        if int(variant) == 3 and not ("actor" in nets and "critic" in nets):
+            variant = 1          # a single network (the critic-only bootstrap step): nothing to interleave
         s = PolicyStep()
         s.B, s.N, s.O, s.E, s.depth, s.action_dim = engine.B, engine.N, engine.O, self.E, self.depth, self.A
         s.t, s.deterministic, s.seed = int(t), 1 if deterministic else 0, int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -119,17 +130,18 @@ class FusedRolloutStep:
                 io.d_hist[k] = P(hist[k]) if hist[k] is not None else None
             assert hid.is_contiguous()
             io.d_emb_out, io.d_hidden, io.d_hidden_out = P(emb), P(hid), None
-            if int(variant) == 2:                            # the two-CTA-per-SM kernel re-reads the previous state: separate output
-                nxt = self._next_hidden.get(name)
+            if int(variant) in (2, 3):                       # these kernels re-read the previous state: separate output buffer
+                # the partner buffer belongs to THIS hidden-state tensor (env-group pipelines step their own states concurrently)
+                nxt = getattr(hid, "_marl_next", None)
                 if nxt is None or nxt.shape != hid.shape or nxt.device != hid.device:
-                    nxt = self._next_hidden[name] = torch.empty_like(hid)
+                    nxt = torch.empty_like(hid)
+                    hid._marl_next = nxt
                 io.d_hidden_out = P(nxt)
-                swaps.append((hid, name))
+                swaps.append((hid, nxt))
             ios[name] = io
         a_w, a_io = (C.byref(self.w["actor"]), C.byref(ios["actor"])) if "actor" in ios else (None, None)
         c_w, c_io = (C.byref(self.w["critic"]), C.byref(ios["critic"])) if "critic" in ios else (None, None)
         _lib.check(self.lib.marl_policy_rollout_step(C.byref(s), a_w, a_io, c_w, c_io, _lib.stream_ptr()),
                    "marl_policy_rollout_step")
-        for hid, name in swaps:                              # the caller's tensor now holds the new state, ours the old buffer
-            nxt = self._next_hidden[name]
+        for hid, nxt in swaps:                               # the caller's tensor now holds the new state, its partner the old buffer
             hid.data, nxt.data = nxt.data, hid.data

@@ -30,6 +30,7 @@ from .normalization import Normalization
 from .replay_buffer import BigBuffer, ReplayBuffer
 
 
+PIPELINE_STAGGER = 0        # env steps by which consecutive env-group pipelines of a rollout are offset (see _rollout_pipelined)
 TWO_STREAM_TRAIN = True     # actor and critic branches of a training minibatch on two CUDA streams
 import os as _os
 CONCURRENT_MINIBATCHES = int(_os.environ.get("MARL_CONCURRENT_MB", "3"))  # minibatches of an epoch in flight at once (their clip-accumulate order is replayed afterwards)
@@ -809,10 +810,19 @@ class MAPPO:
         class _View:                                     # what FusedRolloutStep.step reads from an engine, for envs [lo, hi)
             pass
 
+        # Stagger: every group replans at the same env steps (t % difficulty == 0), and a replan stalls its group for the length of
+        # its slowest A* search; groups that run in lockstep would all be stalled at once.  Group g therefore starts when group g-1
+        # has launched its policy step number `stagger`: the stalls then fall on different wall-clock times and the other groups'
+        # policy kernels fill the SMs meanwhile.
+        stagger = int(os.environ.get("MARL_STAGGER", PIPELINE_STAGGER))
+        stagger_ev = None
         for g in range(G):
             lo, hi = g * B // G, (g + 1) * B // G
             st, side = engine._pipe_streams[2 * g], engine._pipe_streams[2 * g + 1]
             st.wait_event(fork)
+            if stagger_ev is not None:
+                st.wait_event(stagger_ev)
+                stagger_ev = None
             with torch.cuda.stream(st):
                 view = _View()
                 view.B, view.N, view.O = hi - lo, N, engine.O
@@ -848,6 +858,9 @@ class MAPPO:
                         view, oxy_i, o_count, t, seed, deterministic, h_t, h_t, hist_a[t + D][sl], hist_c[t + D][sl], ha, hc,
                         act[t][sl], logp[t][sl], v[t][sl], row_offset=lo * N, tile_rows=full_tile,
                         debug=dbg[t, g] if dbg is not None else None))
+                    if stagger > 0 and t == min(stagger, T - 1) - 1 and g + 1 < G:
+                        stagger_ev = torch.cuda.Event()
+                        stagger_ev.record(st)
                     if join is not None:
                         st.wait_event(join)
                     timed("rollout_kernel", st, lambda: engine._closed_chunk(arena, rec_ptrs, lo, hi, t, 1, act[t:t + 1], 0, seed, st))

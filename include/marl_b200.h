@@ -400,7 +400,8 @@ typedef struct marl_policy_net_io {
 typedef struct marl_policy_step {
     int32_t B, N, O, E, depth, action_dim, t, deterministic;
     int32_t force_action;        /* != 0: d_action is an INPUT (teacher forcing); d_logp is the log-prob of that action */
-    int32_t variant;             /* 0 = choose; 1 = one CTA per SM (16 worker warps); 2 = two CTAs per SM (needs d_hidden_out) */
+    int32_t variant;             /* 0 = choose; 1 = one (tile, network) item per CTA (16 worker warps); 2 = two CTAs per SM; 3 = the actor and
+                                    the critic chain of a tile interleaved in one CTA (both networks given); 2 and 3 need d_hidden_out */
     uint64_t seed;               /* sampling: same counter RNG as marl_act_head (keyed by seed, row, t) */
     const double *d_p_state;     /* [B,N,4] */
     const double *d_e_state;     /* [B,4] */

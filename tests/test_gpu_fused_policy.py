@@ -33,7 +33,7 @@ def _words(packed_bytes, n_bits):
     return np.ascontiguousarray(b).view(np.uint32).astype(np.int64).astype(np.uint32).view(np.int32).reshape(*packed_bytes.shape[:-1], nw)
 
 
-@pytest.mark.parametrize("variant", [1, 2], ids=["one_cta_per_sm", "two_ctas_per_sm"])
+@pytest.mark.parametrize("variant", [1, 2, 3], ids=["one_cta_per_sm", "two_ctas_per_sm", "actor_critic_pair_cta"])
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-4] for p in FIXTURES])
 def test_fused_step_reproduces_reference_rollout_buffer(path, variant):
     from distributed_multi_agent_reinforcement_learning_b200.fused_policy import FusedRolloutStep
@@ -74,7 +74,7 @@ def test_fused_step_reproduces_reference_rollout_buffer(path, variant):
         torch.testing.assert_close(logp, cu(fx["a_logprob_n"][:, t]), **tol)
 
 
-@pytest.mark.parametrize("variant", [1, 2], ids=["one_cta_per_sm", "two_ctas_per_sm"])
+@pytest.mark.parametrize("variant", [1, 2, 3], ids=["one_cta_per_sm", "two_ctas_per_sm", "actor_critic_pair_cta"])
 @pytest.mark.parametrize("B,N,D,steps", [(300, 8, 1, 4), (70, 5, 3, 5), (9, 16, 2, 3), (7, 20, 1, 2), (45, 4, 1, 3)])
 def test_fused_step_matches_unfused_kernels(B, N, D, steps, variant):
     from distributed_multi_agent_reinforcement_learning_b200 import policy_ops as ops
@@ -145,7 +145,10 @@ def test_fused_step_matches_unfused_kernels(B, N, D, steps, variant):
             hc_h, val2 = hc.clone(), torch.empty(B, N, device=dev)
             fused.step(env, oxy_i, o_count, t, 77, False, hist_in, hist_in, emb_a, emb_c, ha_g, hc_h, None, None, val2,
                        nets=("critic",), variant=variant)
-            torch.testing.assert_close(val2, value, rtol=0, atol=0)
+            if variant == 3:      # the single-network launch runs the one-chain kernel: same products, but the value's 128-term dot is summed in another order
+                torch.testing.assert_close(val2, value, rtol=1e-6, atol=2e-7)
+            else:
+                torch.testing.assert_close(val2, value, rtol=0, atol=0)
             ha, hc = ha_ref, hc_ref
             hist_in = [ec.view(B, N, E)] + hist_in[:-1] if D > 1 else [ec.view(B, N, E)]
             env.rollout_closed(arena, 1, t0=t, action_tape=a_ref.view(1, B, N).contiguous(), env_t0=t)

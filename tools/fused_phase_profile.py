@@ -55,6 +55,13 @@ for s_ in np.unique(sm[ok]):
     if s_ == 0:
         print("SM 0 schedule (start us, dur us):", [(round((g0[i] - g0[ok].min()) / 1e3, 1), round((g1[i] - g0[i]) / 1e3, 1)) for i in idx])
 print(f"gap between consecutive CTAs on an SM: median {np.median(gaps) / 1e3:.2f} us, max {np.max(gaps) / 1e3:.2f} us; CTAs per SM: {ok.sum() / len(np.unique(sm[ok])):.2f}")
+if int(os.environ.get("MARL_VARIANT", "0")) == 3:
+    d = d[d[:, 12] > 0]
+    tot = d[:, 12]
+    print(f"pair items {len(d)}; per-item worker cycles: mean {tot.mean():.0f} min {tot.min():.0f} max {tot.max():.0f}; sum/148 = {tot.sum() / 148:.0f}")
+    for i, n in ((0, "messages"), (1, "epi_store"), (2, "fcra"), (3, "fill_x"), (4, "cell halves"), (5, "head"), (11, "wait mma")):
+        print(f"   {n:14s} {d[:, i].mean():10.0f} cycles ({100 * d[:, i].mean() / tot.mean():5.1f}%)")
+    sys.exit(0)
 names = ["msg0", "msg1", "msg2", "epi_av(x3)", "epi_sem", "fcra", "epi_aggf", "epi_f", "load_hidden(x2)", "epi_cell(x2)", "head",
          "wait_mma(all)", "total"]
 d = d[d[:, 12] > 0]            # CTAs that ran (critic items first, then the actor's)
