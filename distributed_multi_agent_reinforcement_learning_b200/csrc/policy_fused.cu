@@ -199,6 +199,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -590,43 +602,44 @@ __device__ void phase_msg_fast(const Ctx &c, int rel)
                     }
                 }
             } else {
-                // this warp's 16 rows x OW adjacency words: lane l holds word l of the group's flattened [NA][OW] block(s)
+                // this group's NA rows x OW adjacency words: lane l holds words l, l + 32, ... of the flattened [NA][OW] block.  An
+                // agent sees one or two boundary cells on average, so almost every word is zero: a ballot of the non-zero words
+                // lets a row visit only those (same cells in the same ascending order as a plain scan of all OW words).
                 uint32_t my_bits[4];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int idx = lane + 32 * t;
                     my_bits[t] = idx < NA * a->OW ? a->o_adj[gr0 * a->OW + idx] : 0u;
                 }
+                uint32_t nz[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) nz[t] = __ballot_sync(0xffffffffu, my_bits[t] != 0u);
 #pragma unroll 1
                 for (int i = 0; i < NA; ++i) {
-                    const float4 pi = c.s_p[r0 + i];
-                    float cc[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) cc[q] = dot4w(reinterpret_cast<const float(&)[4]>(w[q]), pi.x, pi.y, pi.z, pi.w, b[q]);
+                    float cc[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
                     int cnt = 0;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
+                    bool have_cc = false;
+#pragma unroll 1
+                    for (int t = 0; t < a->OW; ++t) {
                         const int idx = i * a->OW + t;
-                        uint32_t bits = 0u;
-                        if (t < a->OW) {
-                            const uint32_t v0 = __shfl_sync(0xffffffffu, my_bits[0], idx & 31), v1 = __shfl_sync(0xffffffffu, my_bits[1], idx & 31);
-                            const uint32_t v2 = __shfl_sync(0xffffffffu, my_bits[2], idx & 31), v3 = __shfl_sync(0xffffffffu, my_bits[3], idx & 31);
-                            bits = (idx >> 5) == 0 ? v0 : ((idx >> 5) == 1 ? v1 : ((idx >> 5) == 2 ? v2 : v3));
+                        const uint32_t nzw = (idx >> 5) == 0 ? nz[0] : ((idx >> 5) == 1 ? nz[1] : ((idx >> 5) == 2 ? nz[2] : nz[3]));
+                        if (!((nzw >> (idx & 31)) & 1u)) continue;                     // warp-uniform
+                        const uint32_t v0 = __shfl_sync(0xffffffffu, my_bits[0], idx & 31), v1 = __shfl_sync(0xffffffffu, my_bits[1], idx & 31);
+                        const uint32_t v2 = __shfl_sync(0xffffffffu, my_bits[2], idx & 31), v3 = __shfl_sync(0xffffffffu, my_bits[3], idx & 31);
+                        uint32_t bits = (idx >> 5) == 0 ? v0 : ((idx >> 5) == 1 ? v1 : ((idx >> 5) == 2 ? v2 : v3));
+                        if (!have_cc) {
+                            const float4 pi = c.s_p[r0 + i];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) cc[q] = dot4w(reinterpret_cast<const float(&)[4]>(w[q]), pi.x, pi.y, pi.z, pi.w, b[q]);
+                            have_cc = true;
                         }
                         cnt += __popc(bits);
-                        while (bits) {                                                    // warp-uniform; two cells per trip, in bit order
+                        while (bits) {                                                    // warp-uniform, in bit order
                             const int k0 = __ffs(bits) - 1;
                             bits &= bits - 1;
-                            const bool two = bits != 0u;
-                            const int k1 = two ? __ffs(bits) - 1 : k0;
-                            bits &= bits - 1;
-                            const float2 o0 = so[32 * t + k0], o1 = so[32 * t + k1];
+                            const float2 o0 = so[32 * t + k0];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) acc[q] += fmaxf(cc[q] - fmaf(w[q][1], o0.y, w[q][0] * o0.x), 0.f);
-                            if (two) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) acc[q] += fmaxf(cc[q] - fmaf(w[q][1], o1.y, w[q][0] * o1.x), 0.f);
-                            }
                         }
                     }
                     const float nrm = cnt ? 1.f / fmaxf((float)cnt, 1e-12f) : 0.f;
@@ -1297,23 +1310,124 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
 // CTA the 16 worker warps idle while the tensor pipe runs (~30 % of an item) and the tensor pipe idles while they work.
 // Here the workers alternate between the two chains: they finish a step of the actor chain, hand its tile to the issuer, and do
 // the same step of the critic chain while the actor's MMAs run, and vice versa - the same 16 warps at 8 rows each (the code
-// that fits 96 registers), so unlike two co-resident CTAs nothing is paid in registers or shared memory per warp.
-//   shared memory : X_actor 64 KB + X_critic 64 KB + weight ring 2 x 32 KB + boundary-cell staging 32 KB + 3 KB   (227 KB)
+// that fits 96 registers), so unlike two co-resident CTAs nothing is paid in registers or shared memory per warp.  And because
+// the two networks share ONE encoder (DHGN/mappo_parallel.py:582-616) and the CTA holds the same rows for both, everything the
+// two chains have in common is computed once: the fp32 copy of the states, the staged boundary cells, relation 0's q_j / a_i and
+// its pair terms relu(a_i - q_j) (reduced under the comm-adjacency mask for the actor and unmasked for the critic in the same
+// loop), relation 1's message (times e_adj for the actor).
+//   shared memory : X_actor 64 KB + X_critic 64 KB + weight ring 64 KB + boundary-cell staging 32 KB + 3 KB        (227 KB)
 //   tensor memory : 256 columns per chain.  The encoder needs two 128-column accumulators; the GRU runs in two 64-column halves
-//                   (r @0, z @64, n_i @128, n_h @192) with x and h_prev re-staged in X for each half (they come back from L2),
-//                   the new state written straight from registers to the OUTPUT hidden buffer (the caller ping-pongs).
-//   both chains share the fp32 copy of the tile's states and the staged boundary cells; each has its own pair of mbarriers.
-// The loader and the issuer walk the two unit programs group by group in the same order as the workers: A.g0, C.g0, A.g1, ...
+//                   (r @0, z @64, n_i @128, n_h @192) in the order  W_ih(half 0) | X <- h_prev | W_hh(half 0) -> cell 0 |
+//                   W_hh(half 1) | X <- x | W_ih(half 1) -> cell 1 | X <- h',  i.e. three X fills per layer whose global loads are
+//                   issued BEFORE the wait for the running MMA group; the new state goes straight from registers to memory (in
+//                   place: a half only overwrites columns nobody reads from memory afterwards).
+//   weight ring   : a FIFO of 16 KB slots; a k-block of a 128-row unit takes two slots, of a 64-row GRU unit one, so the ring holds
+//                   one whole encoder unit or two GRU units ahead of the issuer.
+// The loader and the issuer walk the two unit programs group by group in the order the workers signal them: A.g0, C.g0, A.g1, ...
 struct MemPair {
-    static constexpr int NST = 2, STAGE = WSTAGE;
-    static constexpr int XC_OFF = X_BYTES, RING_OFF = 2 * X_BYTES, MISC_OFF = RING_OFF + NST * STAGE, OXY_OFF = MISC_OFF + MISC_BYTES;
+    static constexpr int SLOT = 16384, NSLOT = 4, NENT = 8;
+    static constexpr int XC_OFF = X_BYTES, RING_OFF = 2 * X_BYTES, MISC_OFF = RING_OFF + NSLOT * SLOT, OXY_OFF = MISC_OFF + MISC_BYTES;
     static constexpr int BYTES = OXY_OFF + OXY_BYTES;
-    static constexpr int BAR_READY = 2 * NST, BAR_DONE = 2 * NST + 2;      // [chain]
+    static constexpr int BAR_FULL = 0, BAR_EMPTY = NENT, BAR_READY = 2 * NENT, BAR_DONE = 2 * NENT + 2, NBAR = 2 * NENT + 4;   // [chain]
 };
 static_assert(MemPair::BYTES <= 232448, "PAIR kernel shared memory");
+static_assert((MemPair::NBAR + 2) * 8 % 16 == 0 && (MemPair::NBAR + 2) * 8 + (ROWS + 32) * 16 <= MISC_BYTES, "PAIR kernel misc block");
 
-// one 64-column half of the GRU cell for WW worker warps: thread <-> row 32*(warp&3)+lane, columns [CPH*(warp>>2), +CPH) of the half
-template <int WW>
+// ring bookkeeping shared by the loader and the issuer (both walk the same unit lists, so both compute the same slots)
+struct RingCursor {
+    int cur = 0, seq = 0;
+    __device__ __forceinline__ void next(uint32_t bytes, int &slot, int &k, int &e)
+    {
+        k = bytes > (uint32_t)MemPair::SLOT ? 2 : 1;
+        if (k == 2 && (cur & 1)) ++cur;                    // two-slot entries start on an even slot (never wrap)
+        slot = cur & (MemPair::NSLOT - 1);
+        cur += k;
+        e = seq++;
+    }
+};
+
+// ---- relations 0 and 1 for BOTH chains at once (env-grouped fast path, N = NA in {4, 8}): same arithmetic, term for term, as
+// phase_msg_fast run once per network - the pair terms / the evader message are simply not computed twice
+template <int NA, int WW>
+__device__ void phase_msg_pair01(const Ctx &c, unsigned char *XA, unsigned char *XC, int rel)
+{
+    constexpr int RPW = Lay<WW>::RPW;
+    static_assert(RPW % NA == 0, "whole envs per warp");
+    const StepArgs *a = c.a;
+    const int lane = c.lane;
+    float w[4][8], b[4];
+    load_msg_weights(c.na, rel, lane, w, b);
+#pragma unroll 1
+    for (int g = 0; g < RPW / NA; ++g) {
+        const int r0 = RPW * c.warp + g * NA;
+        int64_t gr0;
+        int env, i0;
+        const bool ok = row_info(c, r0, gr0, env, i0);
+        if (!ok) {
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                x_store4(XA, r0 + i, lane, make_float4(0.f, 0.f, 0.f, 0.f));
+                x_store4(XC, r0 + i, lane, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+            continue;
+        }
+        const float4 ev = c.s_e[r0 / NA];
+        if (rel == 0) {
+            float qj[NA][4];
+            float4 pj[NA];
+#pragma unroll
+            for (int j = 0; j < NA; ++j) {
+                pj[j] = c.s_p[r0 + j];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) qj[j][q] = fmaf(w[q][3], pj[j].w, fmaf(w[q][2], pj[j].z, fmaf(w[q][1], pj[j].y, w[q][0] * pj[j].x)));
+            }
+            const uint32_t my_word = lane < NA ? a->p_adj[(gr0 + lane) * a->NW] : 0u;
+            const float nrm_c = 1.f / fmaxf((float)NA, 1e-12f);
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                const uint32_t word = __shfl_sync(0xffffffffu, my_word, i);
+                const int cnt = __popc(word & ((1u << NA) - 1u));
+                const float dex = pj[i].x - ev.x, dey = pj[i].y - ev.y, dez = pj[i].z - ev.z, dew = pj[i].w - ev.w;
+                float ai[4], acc_a[4], acc_c[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    ai[q] = (qj[i][q] + fmaf(w[q][7], dew, fmaf(w[q][6], dez, fmaf(w[q][5], dey, w[q][4] * dex)))) + b[q];
+                    acc_a[q] = acc_c[q] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < NA; ++j) {
+                    const bool on = (word >> j) & 1u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float t = fmaxf(ai[q] - qj[j][q], 0.f);
+                        acc_c[q] += t;
+                        acc_a[q] += on ? t : 0.f;
+                    }
+                }
+                const float nrm_a = cnt ? 1.f / fmaxf((float)cnt, 1e-12f) : 0.f;
+                x_store4(XA, r0 + i, lane, make_float4(acc_a[0] * nrm_a, acc_a[1] * nrm_a, acc_a[2] * nrm_a, acc_a[3] * nrm_a));
+                x_store4(XC, r0 + i, lane, make_float4(acc_c[0] * nrm_c, acc_c[1] * nrm_c, acc_c[2] * nrm_c, acc_c[3] * nrm_c));
+            }
+        } else {
+            const float my_on = lane < NA ? (float)a->e_adj[gr0 + lane] : 1.f;
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                const float4 pi = c.s_p[r0 + i];
+                const float e_on = __shfl_sync(0xffffffffu, my_on, i);
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    o[q] = fmaxf(dot4w(reinterpret_cast<const float(&)[4]>(w[q]), pi.x - ev.x, pi.y - ev.y, pi.z - ev.z, pi.w - ev.w, b[q]), 0.f);
+                x_store4(XA, r0 + i, lane, make_float4(e_on * o[0], e_on * o[1], e_on * o[2], e_on * o[3]));
+                x_store4(XC, r0 + i, lane, make_float4(1.f * o[0], 1.f * o[1], 1.f * o[2], 1.f * o[3]));
+            }
+        }
+    }
+}
+
+// one 64-column half of the GRU cell for WW worker warps: thread <-> row 32*(warp&3)+lane, columns [CPH*(warp>>2), +CPH) of the half.
+// h_prev comes from X (HP_FROM_X: X holds h_prev) or from memory (X holds x by then); the new state goes from registers to memory.
+template <int WW, bool HP_FROM_X>
 __device__ void epi_cell_half_w(const Ctx &c, int l, int half, bool want_value, float *s_part)
 {
     constexpr int CG = WW / 4, CPH = 64 / CG;
@@ -1325,6 +1439,7 @@ __device__ void epi_cell_half_w(const Ctx &c, int l, int half, bool want_value, 
     int env, i;
     const bool ok = row_info(c, row, gr, env, i);
     float *dst = na->hidden_out + ((int64_t)l * c.a->R + gr) * E;
+    const float *hsrc = na->hidden_in + ((int64_t)l * c.a->R + gr) * E;
     float vdot = 0.f;
 #pragma unroll 1
     for (int j0 = CPH * hh; j0 < CPH * hh + CPH; j0 += 8) {
@@ -1339,7 +1454,13 @@ __device__ void epi_cell_half_w(const Ctx &c, int l, int half, bool want_value, 
                      : "=r"(ahn[0]), "=r"(ahn[1]), "=r"(ahn[2]), "=r"(ahn[3]), "=r"(ahn[4]), "=r"(ahn[5]), "=r"(ahn[6]), "=r"(ahn[7]) : "r"(taddr + (uint32_t)(192 + j0)));
         const int col = 64 * half + j0;
         float hp[8];
-        x_load8(c.X, row, col >> 3, hp);
+        if constexpr (HP_FROM_X) {
+            x_load8(c.X, row, col >> 3, hp);
+        } else {
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+            if (ok) { u = *reinterpret_cast<const float4 *>(hsrc + col); v = *reinterpret_cast<const float4 *>(hsrc + col + 4); }
+            hp[0] = u.x; hp[1] = u.y; hp[2] = u.z; hp[3] = u.w; hp[4] = v.x; hp[5] = v.y; hp[6] = v.z; hp[7] = v.w;
+        }
         tmem_wait_ld();
         float hn[8];
 #pragma unroll
@@ -1370,30 +1491,38 @@ __device__ void epi_cell_half_w(const Ctx &c, int l, int half, bool want_value, 
     if (want_value) s_part[(half * CG + hh) * ROWS + row] = vdot;
 }
 
-template <int WW>
-__global__ void __launch_bounds__(Lay<WW>::THREADS, 1)
+// Launched with WW + 4 warps: the worker warps (whole warpgroups) take the registers that the loader / issuer warpgroup (two working
+// lanes, two idle warps) gives back with setmaxnreg, so the SIMT phases get 112 registers per thread instead of 96.
+constexpr int PAIR_WORKER_REGS = 104, PAIR_OTHER_REGS = 56;   // the CTA owns 640 x 96 registers: 512 x 104 + 128 x 56 fits; the issuer lane needs ~50
+// PROF: per-phase cycle counters in registers (tools/fused_phase_profile.py, MARL_POLICY_PROFILE=1); the production instantiation
+// only writes the CTA's start / end %globaltimer, SM id and total cycles when a debug buffer is given, and keeps nothing live for it.
+#define PP_TICK(slot) do { if constexpr (PROF) { const long long now_ = clock64(); tk[slot] += now_ - t_prev; \
+    if (a.dbg && threadIdx.x == 0 && pp_s < 32) { const int kind_ = (slot) == 9 ? 0 : ((slot) == 11 ? 1 : ((slot) == 10 ? 3 : 2)); \
+        a.dbg[((size_t)gridDim.x + 16 * blockIdx.x + 4 * kind_) * 16 + 2 * pp_s + pp_ch] += now_ - t_prev; } \
+    t_prev = now_; } } while (0)
+template <int WW, bool PROF>
+__global__ void __launch_bounds__((WW + 4) * 32, 1)
 policy_pair_kernel(const __grid_constant__ StepArgs a)
 {
     using M = MemPair;
-    constexpr int NST = M::NST;
     extern __shared__ __align__(1024) unsigned char smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     unsigned char *Wst = smem + M::RING_OFF;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + M::MISC_OFF);   // full[2], empty[2], a_ready[2 chains], mma_done[2 chains]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NST + 4);
-    float4 *s_p = reinterpret_cast<float4 *>(bars + 16);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + M::MISC_OFF);   // full[8], empty[8], a_ready[2 chains], mma_done[2 chains]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + M::NBAR);
+    float4 *s_p = reinterpret_cast<float4 *>(bars + M::NBAR + 2);                 // 16-byte aligned
     float4 *s_e = s_p + ROWS;
     float2 *s_oxy = reinterpret_cast<float2 *>(smem + M::OXY_OFF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NST; ++s) {
-            mbar_init(smem_u32(&bars[s]), 1);
-            mbar_init(smem_u32(&bars[NST + s]), 1);
+        for (int e = 0; e < M::NENT; ++e) {
+            mbar_init(smem_u32(&bars[M::BAR_FULL + e]), 1);
+            mbar_init(smem_u32(&bars[M::BAR_EMPTY + e]), 1);
         }
         for (int ch = 0; ch < 2; ++ch) {
-            mbar_init(smem_u32(&bars[M::BAR_READY + ch]), Lay<WW>::WORKERS);
+            mbar_init(smem_u32(&bars[M::BAR_READY + ch]), WW);            // one arrival per worker warp
             mbar_init(smem_u32(&bars[M::BAR_DONE + ch]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1406,6 +1535,8 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp < WW) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PAIR_WORKER_REGS));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PAIR_OTHER_REGS));
 
     if (warp < WW) {
         // ================================================================================= workers
@@ -1426,76 +1557,110 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
             }
             worker_sync<WW>();
         }
-        long long tk[16];
+        long long tk[PROF ? 12 : 1];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) tk[q] = 0;
-        long long t_prev = clock64();
-        const long long t_begin = t_prev;
+        for (int q = 0; q < (PROF ? 12 : 1); ++q) tk[q] = 0;
+        long long t_prev = PROF ? clock64() : 0;
+        (void)tk; (void)t_prev;
         if (a.dbg && threadIdx.x == 0) {
             unsigned long long gt;
             unsigned smid;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
             asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-            tk[13] = (long long)gt;
-            tk[15] = (long long)smid;
+            long long *d = a.dbg + (size_t)blockIdx.x * 16;
+            d[12] = clock64();
+            d[13] = (long long)gt;
+            d[15] = (long long)smid;
         }
         const int D = a.depth, G0 = 7 + 3 * D, S_ACTOR = G0 + 9, S_CRITIC = G0 + 8;
+        const bool pair01 = (a.N == 8 || a.N == 4) && a.NW == 1;      // relations 0 and 1 computed once for both chains
+        const uint32_t bar_ready0 = smem_u32(&bars[M::BAR_READY]), bar_done0 = smem_u32(&bars[M::BAR_DONE]);
 #pragma unroll 1
         for (int s = 0; s < S_ACTOR; ++s) {
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
                 if (s >= (ch == 0 ? S_ACTOR : S_CRITIC)) continue;
+                const int pp_s = s, pp_ch = ch;
+                (void)pp_s; (void)pp_ch;
+                const bool shared = pair01 && (s == 0 || s == 2);
+                if (shared && ch == 1) continue;               // done together with the actor's
                 const NetArgs *na = &a.net[ch];
                 c.na = na;
                 c.X = smem + ch * M::XC_OFF;
                 c.tmem = tmem_base + 256u * (uint32_t)ch;
-                c.bar_a_ready = smem_u32(&bars[M::BAR_READY + ch]);
-                c.bar_mma_done = smem_u32(&bars[M::BAR_DONE + ch]);
-                if (s > 0) {                                   // the chain's previous MMA group: accumulators ready, X free again
-                    mbar_wait(c.bar_mma_done, (uint32_t)((s - 1) & 1));
-                    tc_fence_after();
-                }
-                PF_TICK(11);
+                c.bar_a_ready = bar_ready0 + 8u * (uint32_t)ch;
+                c.bar_mma_done = bar_done0 + 8u * (uint32_t)ch;
+                // The chain's previous MMA group must have finished before this step touches its accumulators or X.  Steps that fill X
+                // from memory issue their global loads first and wait afterwards (the load latency hides behind the wait); loads and
+                // stores stay in one straight-line block so that the rows live in registers, not on the stack.
+                auto wait_prev = [&]() {
+                    PP_TICK(9);
+                    if (s > 0) {
+                        mbar_wait(c.bar_mma_done, (uint32_t)((s - 1) & 1));
+                        if (shared) mbar_wait(bar_done0 + 8u, (uint32_t)((s - 1) & 1));
+                        tc_fence_after();
+                    }
+                    PP_TICK(11);
+                };
                 bool signal = true;
                 if (s < 6) {
-                    if ((s & 1) == 0) { phase_msg<WW>(c, s >> 1); PF_TICK(0); }                          // messages of relation s/2 -> X
-                    else { epi_store<WW>(c, 0, na->b_av, true, nullptr, 0, nullptr); PF_TICK(1); }      // AGG_vertex_0 output -> X
+                    wait_prev();
+                    if ((s & 1) == 0) {                        // messages of relation s/2 -> X
+                        if (shared) {
+                            if (a.N == 8) phase_msg_pair01<8, WW>(c, smem, smem + M::XC_OFF, s >> 1);
+                            else phase_msg_pair01<4, WW>(c, smem, smem + M::XC_OFF, s >> 1);
+                        } else {
+                            phase_msg<WW>(c, s >> 1);
+                        }
+                        PP_TICK(0);
+                    } else {                                   // AGG_vertex_0 output -> X
+                        epi_store<WW>(c, 0, na->b_av, true, nullptr, 0, nullptr);
+                        PP_TICK(1);
+                    }
                 } else if (s == 6) {
+                    wait_prev();
                     epi_store<WW>(c, 128, na->b_sem, false, na->sem_w, na->sem_ld, nullptr);             // h0 (no activation)
-                    PF_TICK(1);
+                    PP_TICK(1);
                 } else if (s < G0) {
                     const int k = (s - 7) / 3, sub = (s - 7) % 3;
                     if (sub == 0) {
                         float4 pre[Lay<WW>::RPW];
                         uint32_t words[4] = {0u, 0u, 0u, 0u};
                         phase_fcra_prefetch<WW>(c, k, pre, words);
+                        wait_prev();
                         phase_fcra_finish<WW>(c, k, pre, words);
-                        PF_TICK(2);
+                        PP_TICK(2);
                     } else if (sub == 1) {
+                        wait_prev();
                         epi_store<WW>(c, 0, na->b_aggf[k], true, nullptr, 0, nullptr);
-                        PF_TICK(1);
+                        PP_TICK(1);
                     } else {
+                        wait_prev();
                         epi_store<WW>(c, 128, na->b_f[k], true, nullptr, 0, k == D - 1 ? na->emb_out : nullptr);
-                        PF_TICK(1);
+                        PP_TICK(1);
                     }
                 } else if (s < G0 + 8) {
-                    const int l = (s - G0) >> 2, sub = (s - G0) & 3;
-                    const float *h_src = na->hidden_in + (int64_t)l * a.R * E;
-                    if ((sub & 1) == 0) {                      // W_ih group of this half done: X <- h_prev for the W_hh group
-                        fill_x<WW>(c, h_src);
-                        PF_TICK(3);
-                    } else {
-                        const int half = sub >> 1;
-                        const bool want_value = l == 1 && na->head_w_eff != nullptr;
-                        epi_cell_half_w<WW>(c, l, half, want_value, c.s_val);
-                        worker_sync<WW>();                     // every reader of h_prev in X is done; the half's new state is in memory
-                        PF_TICK(4);
-                        if (half == 0) {                       // X <- x again for the other half
-                            fill_x<WW>(c, l == 0 ? na->emb_out : na->hidden_out);
-                            PF_TICK(3);
-                        } else if (l == 0 || ch == 0) {        // X <- the layer's new state: input of layer 1 / of the actor head
+                    const int l = (s - G0) >> 2, gsub = (s - G0) & 3;
+                    const bool want_value = l == 1 && na->head_w_eff != nullptr;
+                    if (gsub == 0 || gsub == 2) {              // X <- h_prev (for W_hh of both halves) / X <- x again (for W_ih, half 1)
+                        const float *src = gsub == 0 ? na->hidden_in + (int64_t)l * a.R * E : (l == 0 ? na->emb_out : na->hidden_out);
+                        float4 pre[8];
+                        rows_prefetch8<WW>(c, src, 0, pre);
+                        wait_prev();
+                        rows_store8<WW>(c, 0, pre);
+                        PP_TICK(3);
+                    } else if (gsub == 1) {                    // W_hh(half 0) done: cell of half 0, h_prev read back from X
+                        wait_prev();
+                        epi_cell_half_w<WW, true>(c, l, 0, want_value, c.s_val);
+                        PP_TICK(4);
+                    } else {                                   // W_ih(half 1) done: cell of half 1, h_prev from memory (X holds x)
+                        wait_prev();
+                        epi_cell_half_w<WW, false>(c, l, 1, want_value, c.s_val);
+                        worker_sync<WW>();                     // both halves of the new state are in memory
+                        PP_TICK(4);
+                        if (l == 0 || ch == 0) {               // X <- the layer's new state: input of layer 1 / of the actor head
                             fill_x<WW>(c, na->hidden_out + (int64_t)l * a.R * E);
-                            PF_TICK(3);
+                            PP_TICK(3);
                         } else {                               // critic, last layer: the value
                             signal = false;
                             const int row = 32 * (warp & 3) + lane, hh = warp >> 2;
@@ -1510,28 +1675,42 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
                         }
                     }
                 } else {
+                    wait_prev();
                     epi_head<MARL_NUM_ACTIONS>(c);
-                    PF_TICK(5);
+                    PP_TICK(5);
                     signal = false;
                 }
                 if (signal) {
+                    // every lane makes its X stores visible to the tensor core's proxy and orders its TMEM loads; one lane per warp
+                    // arrives (512 arrivals on one mbarrier serialise: ~1.2 K cycles per hand-over, exposed here because the MMA
+                    // latency itself is hidden behind the other chain's step)
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     tc_fence_before();
-                    mbar_arrive(c.bar_a_ready);
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(c.bar_a_ready);
+                        if (shared) mbar_arrive(bar_ready0 + 8u);
+                    }
+                    PP_TICK(10);
                 }
             }
         }
         if (a.dbg && threadIdx.x == 0) {
-            tk[12] = clock64() - t_begin;
             unsigned long long gt;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-            tk[14] = (long long)gt;
-            for (int q = 0; q < 16; ++q) a.dbg[(size_t)blockIdx.x * 16 + q] = tk[q];
+            long long *d = a.dbg + (size_t)blockIdx.x * 16;
+            d[12] = clock64() - d[12];
+            d[14] = (long long)gt;
+            if constexpr (PROF) {
+                for (int q = 0; q < 6; ++q) d[q] = tk[q];
+                d[9] = tk[9]; d[10] = tk[10]; d[11] = tk[11];
+            }
         }
     } else if (warp == WW) {
         // ================================================================================= weight loader
         if (lane == 0) {
-            int it = 0, iu[2] = {0, 0};
+            RingCursor rc;
+            int owner[M::NSLOT] = {-1, -1, -1, -1}, iu[2] = {0, 0};
             while (iu[0] < a.net[0].n_units || iu[1] < a.net[1].n_units) {
                 for (int ch = 0; ch < 2; ++ch) {
                     const NetArgs *na = &a.net[ch];
@@ -1540,40 +1719,59 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
                         const Unit un = na->u[iu[ch]++];
                         last = un.last != 0;
                         const uint32_t bytes = 2u * un.n_out * 128u;
-                        for (int kb = 0; kb < NKB; ++kb, ++it) {
-                            const int st = it % NST, round = it / NST;
-                            if (round > 0) mbar_wait(smem_u32(&bars[NST + st]), (uint32_t)((round - 1) & 1));
-                            mbar_expect_tx(smem_u32(&bars[st]), bytes);
-                            bulk_g2s(smem_u32(Wst + st * M::STAGE), na->packed + un.off + (size_t)kb * bytes, bytes, smem_u32(&bars[st]));
+                        for (int kb = 0; kb < NKB; ++kb) {
+                            int slot, k, e;
+                            rc.next(bytes, slot, k, e);
+                            int need = owner[slot];
+                            if (k == 2 && owner[slot + 1] > need) need = owner[slot + 1];
+                            if (need >= 0) mbar_wait(smem_u32(&bars[M::BAR_EMPTY + (need & (M::NENT - 1))]), (uint32_t)((need / M::NENT) & 1));
+                            owner[slot] = e;
+                            if (k == 2) owner[slot + 1] = e;
+                            const uint32_t full = smem_u32(&bars[M::BAR_FULL + (e & (M::NENT - 1))]);
+                            mbar_expect_tx(full, bytes);
+                            bulk_g2s(smem_u32(Wst + slot * M::SLOT), na->packed + un.off + (size_t)kb * bytes, bytes, full);
                         }
                     }
                 }
             }
         }
-    } else {
+    } else if (warp == WW + 1) {
         // ================================================================================= MMA issuer
-        if (lane == 0) {
-            int it = 0, iu[2] = {0, 0}, grp[2] = {0, 0};
-            while (iu[0] < a.net[0].n_units || iu[1] < a.net[1].n_units) {
-                for (int ch = 0; ch < 2; ++ch) {
-                    const NetArgs *na = &a.net[ch];
-                    if (iu[ch] >= na->n_units) continue;
-                    mbar_wait(smem_u32(&bars[M::BAR_READY + ch]), (uint32_t)(grp[ch] & 1));
-                    tc_fence_after();
-                    const unsigned char *X = smem + ch * M::XC_OFF;
-                    bool last = false;
-                    while (!last) {
-                        const Unit un = na->u[iu[ch]++];
-                        last = un.last != 0;
-                        const uint32_t idesc = idesc_f16(un.n_out);
-                        const uint32_t acc = tmem_base + 256u * (uint32_t)ch + un.acc_col;
-                        const uint32_t lo_off = (uint32_t)un.n_out * 128u;
-                        for (int kb = 0; kb < NKB; ++kb, ++it) {
-                            const int st = it % NST, round = it / NST;
-                            mbar_wait(smem_u32(&bars[st]), (uint32_t)(round & 1));
-                            tc_fence_after();
-                            const uint32_t xa = smem_u32(X + kb * XKB), wb = smem_u32(Wst + st * M::STAGE);
-                            const uint64_t a_hi0 = make_desc(xa), a_lo0 = make_desc(xa + TILE), b_hi0 = make_desc(wb), b_lo0 = make_desc(wb + lo_off);
+        // The whole warp walks the unit program (warp-uniform control flow, every lane polls the barriers); one elected lane issues.
+        // Under `if (lane == 0)` the compiler has to wrap every tcgen05.mma in a lane-serialising loop to get its operands into
+        // uniform registers (~20 instructions per MMA): too slow for the 64-row GRU units, whose MMAs take 32 cycles each.
+        RingCursor rc;
+        int iu[2] = {0, 0}, grp[2] = {0, 0};
+        long long t_ready = 0, t_full = 0, t0 = PROF ? clock64() : 0, t_start = t0;
+        (void)t_start;
+        while (iu[0] < a.net[0].n_units || iu[1] < a.net[1].n_units) {
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch) {
+                const NetArgs *na = &a.net[ch];
+                if (iu[ch] >= na->n_units) continue;
+                mbar_wait(smem_u32(&bars[M::BAR_READY + ch]), (uint32_t)(grp[ch] & 1));
+                if constexpr (PROF) { const long long n_ = clock64(); t_ready += n_ - t0; t0 = n_; }
+                tc_fence_after();
+                const uint32_t xbase = smem_u32(smem + ch * M::XC_OFF);
+                bool last = false;
+#pragma unroll 1
+                while (!last) {
+                    const Unit un = na->u[iu[ch]++];
+                    last = un.last != 0;
+                    const uint32_t idesc = idesc_f16(un.n_out);
+                    const uint32_t acc = tmem_base + 256u * (uint32_t)ch + un.acc_col;
+                    const uint32_t bytes = 2u * un.n_out * 128u, lo_off = (uint32_t)un.n_out * 128u;
+#pragma unroll 1
+                    for (int kb = 0; kb < NKB; ++kb) {
+                        int slot, k, e;
+                        rc.next(bytes, slot, k, e);
+                        if constexpr (PROF) t0 = clock64();
+                        mbar_wait(smem_u32(&bars[M::BAR_FULL + (e & (M::NENT - 1))]), (uint32_t)((e / M::NENT) & 1));
+                        if constexpr (PROF) { const long long n_ = clock64(); t_full += n_ - t0; t0 = n_; }
+                        tc_fence_after();
+                        const uint32_t xa = xbase + kb * XKB, wb = smem_u32(Wst + slot * M::SLOT);
+                        const uint64_t a_hi0 = make_desc(xa), a_lo0 = make_desc(xa + TILE), b_hi0 = make_desc(wb), b_lo0 = make_desc(wb + lo_off);
+                        if (elect_one()) {
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
                                 const uint64_t a_hi = a_hi0 + 2 * kk, a_lo = a_lo0 + 2 * kk, b_hi = b_hi0 + 2 * kk, b_lo = b_lo0 + 2 * kk;
@@ -1581,12 +1779,21 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
                                 umma_f16(acc, a_lo, b_hi, idesc, 1u);
                                 umma_f16(acc, a_hi, b_lo, idesc, 1u);
                             }
-                            umma_commit(smem_u32(&bars[NST + st]));
+                            umma_commit(smem_u32(&bars[M::BAR_EMPTY + (e & (M::NENT - 1))]));
                         }
+                        __syncwarp();
                     }
-                    umma_commit(smem_u32(&bars[M::BAR_DONE + ch]));
-                    ++grp[ch];
                 }
+                if (elect_one()) umma_commit(smem_u32(&bars[M::BAR_DONE + ch]));
+                __syncwarp();
+                ++grp[ch];
+                if constexpr (PROF) t0 = clock64();
+            }
+        }
+        if constexpr (PROF) {
+            if (a.dbg && lane == 0) {
+                long long *d = a.dbg + (size_t)blockIdx.x * 16;
+                d[6] = t_ready; d[7] = t_full; d[8] = clock64() - t_start;
             }
         }
     }
@@ -1618,7 +1825,7 @@ struct UnitSrc {
     int rows, n_out, k0, acc_col, accumulate, last;
 };
 
-static int build_units(const marl_dhgn_weights *w, int depth, int is_actor, int A, UnitSrc *us, bool dual)
+static int build_units(const marl_dhgn_weights *w, int depth, int is_actor, int A, UnitSrc *us, int mode /* 0 one chain per CTA, 1 two CTAs per SM, 2 pair */)
 {
     int n = 0;
     auto add = [&](const float *W, int64_t ld, int rows, int n_out, int k0, int acc, int accu, int last) {
@@ -1634,7 +1841,16 @@ static int build_units(const marl_dhgn_weights *w, int depth, int is_actor, int 
         add(w->fcra_w[k], 2 * E, E, E, 0, 128, 1, 1);
     }
     for (int l = 0; l < 2; ++l) {
-        if (!dual) {
+        if (mode == 2) {
+            // pair kernel: 64-column halves, accumulators r @0, z @64, n_i @128, n_h @192, in the order
+            // W_ih(half 0) | W_hh(half 0) | W_hh(half 1) | W_ih(half 1): X holds x, h_prev, h_prev, x (one re-staging of each)
+            const float *wi = w->gru_w_ih[l], *wh = w->gru_w_hh[l];
+            const int64_t ro = (int64_t)64 * E, g1 = (int64_t)E * E, g2 = (int64_t)2 * E * E;
+            add(wi, E, 64, 64, 0, 0, 0, 0); add(wi + g1, E, 64, 64, 0, 64, 0, 0); add(wi + g2, E, 64, 64, 0, 128, 0, 1);
+            add(wh, E, 64, 64, 0, 0, 1, 0); add(wh + g1, E, 64, 64, 0, 64, 1, 0); add(wh + g2, E, 64, 64, 0, 192, 0, 1);
+            add(wh + ro, E, 64, 64, 0, 0, 0, 0); add(wh + g1 + ro, E, 64, 64, 0, 64, 0, 0); add(wh + g2 + ro, E, 64, 64, 0, 192, 0, 1);
+            add(wi + ro, E, 64, 64, 0, 0, 1, 0); add(wi + g1 + ro, E, 64, 64, 0, 64, 1, 0); add(wi + g2 + ro, E, 64, 64, 0, 128, 0, 1);
+        } else if (mode == 0) {
             for (int g = 0; g < 3; ++g) add(w->gru_w_ih[l] + (int64_t)g * E * E, E, E, E, 0, 128 * g, 0, g == 2);
             add(w->gru_w_hh[l], E, E, E, 0, 0, 1, 0);
             add(w->gru_w_hh[l] + (int64_t)E * E, E, E, E, 0, 128, 1, 0);
@@ -1710,7 +1926,7 @@ using namespace marl;
 extern "C" int64_t marl_policy_pack_bytes(int32_t depth, int32_t is_actor)
 {
     if (depth < 1 || depth > pf::MAXD) return -1;
-    return 2 * pf::layout_bytes(depth, is_actor);        // both kernel variants' images: [one CTA per SM][two CTAs per SM]
+    return 3 * pf::layout_bytes(depth, is_actor);        // the kernel variants' images: [one chain per CTA][two CTAs per SM][pair]
 }
 
 extern "C" int marl_policy_pack(const marl_dhgn_weights *w, int32_t depth, int32_t is_actor, int32_t action_dim, void *d_packed,
@@ -1721,9 +1937,9 @@ extern "C" int marl_policy_pack(const marl_dhgn_weights *w, int32_t depth, int32
     MARL_REQUIRE(d_packed && ((uintptr_t)d_packed & 1023) == 0, "marl_policy_pack: workspace must be 1024-byte aligned");
     MARL_REQUIRE(!is_actor || (action_dim >= 1 && action_dim <= 16), "marl_policy_pack: action_dim=%d (1..16)", action_dim);
     unsigned char *out = static_cast<unsigned char *>(d_packed);
-    for (int dual = 0; dual < 2; ++dual) {
+    for (int mode = 0; mode < 3; ++mode) {
         pf::UnitSrc us[pf::MAX_UNITS];
-        const int n = pf::build_units(w, depth, is_actor, action_dim, us, dual != 0);
+        const int n = pf::build_units(w, depth, is_actor, action_dim, us, mode);
         for (int u = 0; u < n; ++u) {
             const int total = us[u].n_out * 128;
             pf::pack_unit_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(us[u].W, us[u].ld, us[u].rows, us[u].n_out, us[u].k0, out);
@@ -1735,15 +1951,15 @@ extern "C" int marl_policy_pack(const marl_dhgn_weights *w, int32_t depth, int32
     return MARL_OK;
 }
 
-static int fill_net(pf::NetArgs &na, const marl_dhgn_weights *w, const marl_policy_net_io *io, int depth, int is_actor, int A, bool dual)
+static int fill_net(pf::NetArgs &na, const marl_dhgn_weights *w, const marl_policy_net_io *io, int depth, int is_actor, int A, int mode)
 {
     int rc = pf::check_weights(w, depth, is_actor);
     if (rc) return rc;
     MARL_REQUIRE(io->d_packed && io->d_hidden && io->d_emb_out, "marl_policy_rollout_step: null packed / hidden / emb_out (%s)",
                  is_actor ? "actor" : "critic");
     pf::UnitSrc us[pf::MAX_UNITS];
-    na.n_units = pf::build_units(w, depth, is_actor, A, us, dual);
-    uint32_t off = dual ? (uint32_t)pf::layout_bytes(depth, is_actor) : 0u;
+    na.n_units = pf::build_units(w, depth, is_actor, A, us, mode);
+    uint32_t off = (uint32_t)(mode * pf::layout_bytes(depth, is_actor));
     for (int u = 0; u < na.n_units; ++u) {
         na.u[u] = pf::Unit{off, (uint16_t)us[u].n_out, (uint16_t)us[u].acc_col, (uint8_t)us[u].accumulate, (uint8_t)us[u].last, 0};
         off += (uint32_t)pf::unit_bytes(us[u].n_out);
@@ -1787,11 +2003,12 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
     const bool pingpong = (!has_a || (actor_io->d_hidden_out && actor_io->d_hidden_out != actor_io->d_hidden)) &&
                           (!has_c || (critic_io->d_hidden_out && critic_io->d_hidden_out != critic_io->d_hidden));
     MARL_REQUIRE(s->variant >= 0 && s->variant <= 3, "marl_policy_rollout_step: variant=%d (0..3)", s->variant);
-    MARL_REQUIRE((s->variant != 2 && s->variant != 3) || pingpong, "marl_policy_rollout_step: variant %d needs d_hidden_out != d_hidden", s->variant);
+    MARL_REQUIRE(s->variant != 2 || pingpong, "marl_policy_rollout_step: variant 2 needs d_hidden_out != d_hidden");
     MARL_REQUIRE(s->variant != 3 || (has_a && has_c), "marl_policy_rollout_step: variant 3 (actor + critic chains in one CTA) needs both networks");
     const bool pair = s->variant == 3;
-    const bool dual = pair || s->variant == 2 || (s->variant == 0 && pingpong && pf::kDualByDefault && s->O <= pf::Mem<true>::OXY);
-    a.rows_per_tile = pf::choose_rows_per_tile(a.R, s->N, pair ? 1 : nets, (dual && !pair) ? 2 : 1, s->tile_rows);
+    const bool dual = !pair && (s->variant == 2 || (s->variant == 0 && pingpong && pf::kDualByDefault && s->O <= pf::Mem<true>::OXY));
+    const int mode = pair ? 2 : (dual ? 1 : 0);
+    a.rows_per_tile = pf::choose_rows_per_tile(a.R, s->N, pair ? 1 : nets, dual ? 2 : 1, s->tile_rows);
     a.n_tiles = (int)((a.R + a.rows_per_tile - 1) / a.rows_per_tile);
     a.p_state = s->d_p_state; a.e_state = s->d_e_state; a.oxy = s->d_oxy; a.map_id = s->d_map_id; a.o_count = s->d_o_count;
     a.p_adj = s->d_p_adj_bits; a.e_adj = s->d_e_adj; a.o_adj = s->d_o_adj_bits;
@@ -1799,8 +2016,8 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
     a.row_offset = s->row_offset;
     a.dbg = static_cast<long long *>(s->d_debug);
     int rc;
-    if (has_a) { rc = fill_net(a.net[0], actor_w, actor_io, s->depth, 1, s->action_dim, dual); if (rc) return rc; }
-    if (has_c) { rc = fill_net(a.net[1], critic_w, critic_io, s->depth, 0, s->action_dim, dual); if (rc) return rc; }
+    if (has_a) { rc = fill_net(a.net[0], actor_w, actor_io, s->depth, 1, s->action_dim, mode); if (rc) return rc; }
+    if (has_c) { rc = fill_net(a.net[1], critic_w, critic_io, s->depth, 0, s->action_dim, mode); if (rc) return rc; }
     a.net_count = nets;
     a.net_first = has_a ? 0 : 1;
     const unsigned grid = (unsigned)(a.n_tiles * (pair ? 1 : a.net_count));
@@ -1812,7 +2029,8 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
         return MARL_OK;
     };
     // one CTA per SM: 16 worker warps unless the env-grouped message path needs a whole 16-agent env per warp
-    if (pair) rc = launch(pf::policy_pair_kernel<16>, pf::Lay<16>::THREADS, pf::MemPair::BYTES, false);
+    if (pair && getenv("MARL_POLICY_PROFILE")) rc = launch(pf::policy_pair_kernel<16, true>, (16 + 4) * 32, pf::MemPair::BYTES, false);
+    else if (pair) rc = launch(pf::policy_pair_kernel<16, false>, (16 + 4) * 32, pf::MemPair::BYTES, false);
     else if (dual) rc = launch(pf::policy_step_kernel<8, true>, pf::Lay<8>::THREADS, pf::Mem<true>::BYTES, true);
     else if (!(s->N == 16 && s->O <= pf::OXY_CAP)) rc = launch(pf::policy_step_kernel<16, false>, pf::Lay<16>::THREADS, pf::Mem<false>::BYTES, false);
     else rc = launch(pf::policy_step_kernel<8, false>, pf::Lay<8>::THREADS, pf::Mem<false>::BYTES, false);

@@ -100,8 +100,8 @@ class FusedRolloutStep:
         """hist_*: list (k = 0 newest) of [B,N,E] tensors or None (zeros); emb_*: [B,N,E] outputs; ha/hc: [2,B*N,E] in/out;
         action i32 [B,N], logp / value f32 [B,N] outputs.
         variant: 0 = DEFAULT_VARIANT, 1 = one (tile, network) item per CTA (hidden state updated in place), 2 = two such CTAs per
-        SM, 3 = both networks' chains of a tile interleaved in one CTA.  Variants 2 and 3 read the previous hidden state from one
-        buffer and write the new one to another; afterwards the two tensors trade their storage, so for the caller `ha` / `hc`
+        SM, 3 = both networks' chains of a tile interleaved in one CTA.  Variant 2 reads the previous hidden state from one
+        buffer and writes the new one to another; afterwards the two tensors trade their storage, so for the caller `ha` / `hc`
         are still updated "in place" (views taken before the call keep the old state)."""
         if int(variant) == 0 and DEFAULT_VARIANT == 3 and "actor" in nets and "critic" in nets and not (engine.N == 16 and engine.O <= 256):
             variant = 3          # (16-agent envs keep the 8-worker-warp kernel: their message path needs a whole env per warp)
@@ -130,7 +130,7 @@ class FusedRolloutStep:
                 io.d_hist[k] = P(hist[k]) if hist[k] is not None else None
             assert hid.is_contiguous()
             io.d_emb_out, io.d_hidden, io.d_hidden_out = P(emb), P(hid), None
-            if int(variant) in (2, 3):                       # these kernels re-read the previous state: separate output buffer
+            if int(variant) == 2:                            # the two-CTA-per-SM kernel re-reads the previous state: separate output buffer
                 # the partner buffer belongs to THIS hidden-state tensor (env-group pipelines step their own states concurrently)
                 nxt = getattr(hid, "_marl_next", None)
                 if nxt is None or nxt.shape != hid.shape or nxt.device != hid.device:

@@ -12,6 +12,8 @@ from distributed_multi_agent_reinforcement_learning_b200.fused_policy import Fus
 from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO  # noqa: E402
 from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv  # noqa: E402
 
+if int(os.environ.get("MARL_VARIANT", "0")) == 3:
+    os.environ["MARL_POLICY_PROFILE"] = "1"
 cfg = bench.make_cfg()
 B, M, N, E = bench.B_PER_GPU, 32, bench.N_AGENTS, 128
 wl = bench.host_workload(cfg, B, M, seed=1)
@@ -33,7 +35,7 @@ act, logp, val = torch.zeros(B, N, dtype=torch.int32, device=dev), torch.empty(B
 hist = [0.1 * torch.randn(B, N, E, device=dev)]
 env.observe()
 n_tiles = (B * N + 127) // 128   # upper bound is 4/3 of this (the kernel may pick tiles down to 96 rows)
-dbg = torch.zeros(2 * ((4 * n_tiles + 2) // 3), 16, dtype=torch.int64, device=dev)
+dbg = torch.zeros(24 * ((4 * n_tiles + 2) // 3), 16, dtype=torch.int64, device=dev)
 for it in range(3):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -43,6 +45,9 @@ for it in range(3):
     e.synchronize()
     print("launch ms", s.elapsed_time(e))
 d = dbg.cpu().numpy().astype(np.float64)
+if int(os.environ.get("MARL_VARIANT", "0")) == 3:
+    d_all = d
+    d = d[: int((d[:, 13] > 1e15).sum())]
 # wall-clock schedule of the launch: effective SM clock, gaps between consecutive CTAs of one SM
 g0, g1, sm = d[:, 13], d[:, 14], d[:, 15].astype(int)
 ok = d[:, 12] > 0
@@ -56,11 +61,16 @@ for s_ in np.unique(sm[ok]):
         print("SM 0 schedule (start us, dur us):", [(round((g0[i] - g0[ok].min()) / 1e3, 1), round((g1[i] - g0[i]) / 1e3, 1)) for i in idx])
 print(f"gap between consecutive CTAs on an SM: median {np.median(gaps) / 1e3:.2f} us, max {np.max(gaps) / 1e3:.2f} us; CTAs per SM: {ok.sum() / len(np.unique(sm[ok])):.2f}")
 if int(os.environ.get("MARL_VARIANT", "0")) == 3:
-    d = d[d[:, 12] > 0]
+    grid = len(d)                                 # CTA rows carry a %globaltimer stamp; the per-step rows follow them
+    steps = d_all[grid:grid + 16 * grid].reshape(grid, 4, 64).mean(axis=0).reshape(4, 32, 2) / 3.0      # three launches accumulate
+    for kind, nm in enumerate(("pre/loop", "wait", "work", "signal")):
+        print(f"per-step {nm:9s} (actor/critic):", " ".join(f"{int(x)}/{int(y)}" for x, y in steps[kind][:20]))
+    d = d[:grid]
     tot = d[:, 12]
     print(f"pair items {len(d)}; per-item worker cycles: mean {tot.mean():.0f} min {tot.min():.0f} max {tot.max():.0f}; sum/148 = {tot.sum() / 148:.0f}")
-    for i, n in ((0, "messages"), (1, "epi_store"), (2, "fcra"), (3, "fill_x"), (4, "cell halves"), (5, "head"), (11, "wait mma")):
+    for i, n in ((0, "messages"), (1, "epi_store"), (2, "fcra"), (3, "fill_x"), (4, "cell halves"), (5, "head"), (9, "loop+prefetch"), (10, "signal"), (11, "wait mma")):
         print(f"   {n:14s} {d[:, i].mean():10.0f} cycles ({100 * d[:, i].mean() / tot.mean():5.1f}%)")
+    print(f"   issuer: waiting for the workers {d[:, 6].mean():.0f}, for weights {d[:, 7].mean():.0f}, total {d[:, 8].mean():.0f} -> issuing / idle in MMA queue {d[:, 8].mean() - d[:, 6].mean() - d[:, 7].mean():.0f}")
     sys.exit(0)
 names = ["msg0", "msg1", "msg2", "epi_av(x3)", "epi_sem", "fcra", "epi_aggf", "epi_f", "load_hidden(x2)", "epi_cell(x2)", "head",
          "wait_mma(all)", "total"]
