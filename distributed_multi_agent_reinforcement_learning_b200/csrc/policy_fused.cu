@@ -1603,42 +1603,37 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
                     PP_TICK(11);
                 };
                 bool signal = true;
-                if (s < 6) {
+                // every dense layer's epilogue is the same code with different operands: ONE call site, so that the (large, fully
+                // unrolled) epilogue exists once in the instruction stream instead of once per layer
+                const int fk = s >= 7 ? (s - 7) / 3 : 0, fsub = s >= 7 ? (s - 7) % 3 : -1;
+                const bool is_msg = s < 6 && (s & 1) == 0, is_fcra_fill = s >= 7 && s < G0 && fsub == 0;
+                if (s < G0 && !is_msg && !is_fcra_fill) {
+                    int acc_col = 0;
+                    const float *bias = na->b_av, *wp = nullptr;
+                    float *gout = nullptr;
+                    bool relu = true;
+                    if (s == 6) { acc_col = 128; bias = na->b_sem; relu = false; wp = na->sem_w; }        // h0 (no activation)
+                    else if (s > 6 && fsub == 1) { bias = na->b_aggf[fk]; }
+                    else if (s > 6) { acc_col = 128; bias = na->b_f[fk]; gout = fk == D - 1 ? na->emb_out : nullptr; }
                     wait_prev();
-                    if ((s & 1) == 0) {                        // messages of relation s/2 -> X
-                        if (shared) {
-                            if (a.N == 8) phase_msg_pair01<8, WW>(c, smem, smem + M::XC_OFF, s >> 1);
-                            else phase_msg_pair01<4, WW>(c, smem, smem + M::XC_OFF, s >> 1);
-                        } else {
-                            phase_msg<WW>(c, s >> 1);
-                        }
-                        PP_TICK(0);
-                    } else {                                   // AGG_vertex_0 output -> X
-                        epi_store<WW>(c, 0, na->b_av, true, nullptr, 0, nullptr);
-                        PP_TICK(1);
-                    }
-                } else if (s == 6) {
-                    wait_prev();
-                    epi_store<WW>(c, 128, na->b_sem, false, na->sem_w, na->sem_ld, nullptr);             // h0 (no activation)
+                    epi_store<WW>(c, acc_col, bias, relu, wp, na->sem_ld, gout);
                     PP_TICK(1);
-                } else if (s < G0) {
-                    const int k = (s - 7) / 3, sub = (s - 7) % 3;
-                    if (sub == 0) {
-                        float4 pre[Lay<WW>::RPW];
-                        uint32_t words[4] = {0u, 0u, 0u, 0u};
-                        phase_fcra_prefetch<WW>(c, k, pre, words);
-                        wait_prev();
-                        phase_fcra_finish<WW>(c, k, pre, words);
-                        PP_TICK(2);
-                    } else if (sub == 1) {
-                        wait_prev();
-                        epi_store<WW>(c, 0, na->b_aggf[k], true, nullptr, 0, nullptr);
-                        PP_TICK(1);
+                } else if (is_msg) {
+                    wait_prev();
+                    if (shared) {                              // messages of relation s/2 -> X
+                        if (a.N == 8) phase_msg_pair01<8, WW>(c, smem, smem + M::XC_OFF, s >> 1);
+                        else phase_msg_pair01<4, WW>(c, smem, smem + M::XC_OFF, s >> 1);
                     } else {
-                        wait_prev();
-                        epi_store<WW>(c, 128, na->b_f[k], true, nullptr, 0, k == D - 1 ? na->emb_out : nullptr);
-                        PP_TICK(1);
+                        phase_msg<WW>(c, s >> 1);
                     }
+                    PP_TICK(0);
+                } else if (is_fcra_fill) {
+                    float4 pre[Lay<WW>::RPW];
+                    uint32_t words[4] = {0u, 0u, 0u, 0u};
+                    phase_fcra_prefetch<WW>(c, fk, pre, words);
+                    wait_prev();
+                    phase_fcra_finish<WW>(c, fk, pre, words);
+                    PP_TICK(2);
                 } else if (s < G0 + 8) {
                     const int l = (s - G0) >> 2, gsub = (s - G0) & 3;
                     const bool want_value = l == 1 && na->head_w_eff != nullptr;
