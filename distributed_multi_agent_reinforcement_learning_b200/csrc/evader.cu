@@ -68,9 +68,12 @@ __device__ __forceinline__ SearchSmem carve(unsigned char *smem, int W1, int NOD
     return s;
 }
 
+// Node id = x * 64 + y (H <= 63): decoding a popped node is a shift and a mask instead of an integer division on the search's
+// critical path, and the ids keep heapq's (x, y) tuple order.
+static constexpr int kNodeShift = 6, kNodeStride = 1 << kNodeShift;
 static size_t search_smem_bytes(const EnvDev &c)
 {
-    const int W1 = c.W + 1, H1 = c.H + 1, NODES = W1 * H1;
+    const int W1 = c.W + 1, NODES = W1 * kNodeStride;
     return sizeof(double) * (NODES + kOpenCap) + sizeof(uint64_t) * 3 * W1 + sizeof(uint16_t) * (((NODES + 3) & ~3) + kOpenCap);
 }
 
@@ -110,7 +113,7 @@ __device__ int replan_warp(const EnvDev &c, const SearchSmem &sm, const uint32_t
                            int16_t *__restrict__ path, int path_cap, int &status)
 {
     const int lane = threadIdx.x & 31;
-    const int W = c.W, H = c.H, W1 = W + 1, H1 = H + 1, NODES = W1 * H1;
+    const int W = c.W, H = c.H, W1 = W + 1, H1 = H + 1, NODES = W1 * kNodeStride;
     const uint64_t hmask = (H >= 64) ? ~0ull : ((1ull << H) - 1ull);
     const int cx = pyround(ex), cy = pyround(ey);
     for (int x = lane; x < W1; x += 32) sm.mov[x] = 0ull;
@@ -123,7 +126,7 @@ __device__ int replan_warp(const EnvDev &c, const SearchSmem &sm, const uint32_t
     const int ux = (lane == 0 || lane == 1 || lane == 7) ? -1 : ((lane >= 3 && lane <= 5) ? 1 : 0);   // astar.py:11-12
     const int uy = (lane >= 1 && lane <= 3) ? 1 : ((lane >= 5 && lane <= 7) ? -1 : 0);
     const double diag = sqrt(2.0);   // math.hypot(1, 1)
-    const int start = cx * H1 + cy, goal = tx * H1 + ty;
+    const int start = (cx << kNodeShift) | cy, goal = (tx << kNodeShift) | ty;
     int n_path = 1;
     for (int e = c.e_extend_dis; e >= 0; --e) {
         // ---- Evader.rescan (agent.py:202-230) as column algebra ----
@@ -177,12 +180,15 @@ __device__ int replan_warp(const EnvDev &c, const SearchSmem &sm, const uint32_t
                 }
                 const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
                 const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-                const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
-                const bool cand = (hi == mhi) && (lo == mlo) && best_idx >= 0;
-                const unsigned mnode = __reduce_min_sync(0xffffffffu, cand ? (unsigned)best_node : 0xffffffffu);
-                const unsigned owner_mask = __ballot_sync(0xffffffffu, cand && (unsigned)best_node == mnode);
+                unsigned owner_mask = __ballot_sync(0xffffffffu, hi == mhi && best_idx >= 0);
+                if (__popc(owner_mask) > 1) {            // several lanes share the high word of the smallest f: low word, then the node id
+                    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+                    const bool cand = (hi == mhi) && (lo == mlo) && best_idx >= 0;
+                    const unsigned mnode = __reduce_min_sync(0xffffffffu, cand ? (unsigned)best_node : 0xffffffffu);
+                    owner_mask = __ballot_sync(0xffffffffu, cand && (unsigned)best_node == mnode);
+                }
                 const int owner = __ffs(owner_mask) - 1;
-                const int s = (int)mnode;
+                const int s = __shfl_sync(0xffffffffu, best_node, owner);
                 --n_open;
                 if (lane == owner && best_idx != n_open) {   // remove: move the last entry into the hole
                     sm.of[best_idx] = sm.of[n_open];
@@ -191,23 +197,26 @@ __device__ int replan_warp(const EnvDev &c, const SearchSmem &sm, const uint32_t
                 __syncwarp();
                 if (s == goal) { reached = true; break; }
                 // ---- relax the 8 neighbours (astar.py:56-65) on lanes 0..7 ----
-                const int sx = s / H1, sy = s - sx * H1;
+                const int sx = s >> kNodeShift, sy = s & (kNodeStride - 1);
                 bool push = false;
                 double nf = 0.0;
                 int nn = 0;
                 if (lane < 8) {
                     const int nx = sx + ux, ny = sy + uy;
-                    bool bad = ((sm.blk[sx] >> sy) & 1ull) || nx < 0 || nx > W || ny < 0 || ny > H;
-                    if (!bad) bad = (sm.blk[nx] >> ny) & 1ull;
-                    if (!bad) {
-                        nn = nx * H1 + ny;
-                        const double nc = dadd(sm.g[s], (ux != 0 && uy != 0) ? diag : 1.0);
-                        if (nc < sm.g[nn]) {
-                            sm.g[nn] = nc;
-                            sm.par[nn] = (uint16_t)s;
-                            nf = dadd(nc, dmul(2.5, (double)(abs(tx - nx) + abs(ty - ny))));
-                            push = true;
-                        }
+                    const bool inside = nx >= 0 && nx <= W && ny >= 0 && ny <= H;
+                    // all four shared-memory reads are issued together (clamped indices) instead of one per nested test: the relaxation
+                    // is on the critical path of every pop
+                    const int nxc = inside ? nx : sx, nyc = inside ? ny : sy;
+                    nn = (nxc << kNodeShift) | nyc;
+                    const uint64_t col_s = sm.blk[sx], col_n = sm.blk[nxc];
+                    const double g_s = sm.g[s], g_n = sm.g[nn];
+                    const bool bad = !inside || ((col_s >> sy) & 1ull) || ((col_n >> nyc) & 1ull);
+                    const double nc = dadd(g_s, (ux != 0 && uy != 0) ? diag : 1.0);
+                    if (!bad && nc < g_n) {
+                        sm.g[nn] = nc;
+                        sm.par[nn] = (uint16_t)s;
+                        nf = dadd(nc, dmul(2.5, (double)(abs(tx - nx) + abs(ty - ny))));
+                        push = true;
                     }
                 }
                 const unsigned pm = __ballot_sync(0xffffffffu, push);
@@ -229,8 +238,8 @@ __device__ int replan_warp(const EnvDev &c, const SearchSmem &sm, const uint32_t
                     for (;;) {
                         const int par = sm.par[cur];
                         if (n < path_cap) {
-                            path[2 * n] = (int16_t)(par / H1);
-                            path[2 * n + 1] = (int16_t)(par % H1);
+                            path[2 * n] = (int16_t)(par >> kNodeShift);
+                            path[2 * n + 1] = (int16_t)(par & (kNodeStride - 1));
                         }
                         ++n;
                         cur = par;
@@ -273,7 +282,7 @@ evader_kernel(EnvDev c, EvaderArgs r, int replan_only)
     s.status = 0;
     int16_t *path = r.path + (size_t)b * r.path_cap * 2;
     if (due) {
-        const SearchSmem sm = carve(smem, c.W + 1, (c.W + 1) * (c.H + 1));
+        const SearchSmem sm = carve(smem, c.W + 1, (c.W + 1) * kNodeStride);
         s.plen = replan_warp(c, sm, grid, r.p_state + (size_t)b * c.N * 4, c.N, s.x, s.y, s.tx, s.ty, path, r.path_cap, s.status);
     }
     if (lane == 0) {
