@@ -416,8 +416,14 @@ class RolloutGraph:
 
 
 class MAPPO:
-    def __init__(self, cfg, batch_size, mini_batch_size, agent_type):
+    def __init__(self, cfg, batch_size, mini_batch_size, agent_type, reference_quirks=None):
+        """reference_quirks (default True, or `cfg.algo.reference_quirks`): keep the two reference behaviours that make its rollout
+        forward differ from its training forward at identical weights - the history list that actor and critic
+        alias during the rollout, and the critic's all-ones obstacle adjacency spanning the padded slots in training.  False is the
+        self-consistent variant: per-network histories in the rollout, the map's real boundary cells in training (PPO ratios are then
+        1 on the first epoch); never the parity default."""
         a = cfg.algo
+        self.reference_quirks = bool(getattr(a, "reference_quirks", True)) if reference_quirks is None else bool(reference_quirks)
         self.batch_size, self.mini_batch_size = batch_size, mini_batch_size
         self.max_train_steps, self.lr, self.gamma, self.lamda = a.max_train_steps, a.lr, a.gamma, a.lamda
         self.epsilon, self.K_epochs, self.entropy_coef = a.epsilon, a.epochs, a.entropy_coef
@@ -653,18 +659,22 @@ class MAPPO:
         zeros_hist = torch.zeros(B, N, E, **f32)
         w_eff = None
 
-        def history(t):
-            # one aliased list for both nets (:750-752): newest first = C(t-1), A(t-1), C(t-2), A(t-2), ...
+        quirks = self.reference_quirks
+
+        def history(t, net="actor"):
+            # reference: one aliased list for both nets (:750-752): newest first = C(t-1), A(t-1), C(t-2), A(t-2), ...
+            # actor_only (the evaluator) / reference_quirks=False: each network's own embeddings, newest first
             out = []
             for k in range(D):
-                back = (k + 1) if actor_only else (k // 2 + 1)
-                src = hist_a if actor_only else (hist_c if k % 2 == 0 else hist_a)
+                own = actor_only or not quirks
+                back = (k + 1) if own else (k // 2 + 1)
+                src = (hist_a if (net == "actor" or actor_only) else hist_c) if own else (hist_c if k % 2 == 0 else hist_a)
                 out.append(src[t - back + D] if t - back >= 0 else zeros_hist)
             return out
 
         def critic_step(t, graph):
             nonlocal hc, w_eff
-            emb_c = enc.encode(graph, True, history(t))
+            emb_c = enc.encode(graph, True, history(t, "critic"))
             feat_c, hc = self.critic.features(emb_c.view(1, B * N, E), hc)
             w, _ = self.critic.head_weight()
             w_eff = w.reshape(E).contiguous()
@@ -722,8 +732,8 @@ class MAPPO:
                     join = torch.cuda.Event()
                     join.record(side)
                 timed("env_observe_kernel", engine.observe)
-                h_t = none_if_zero(history(t))
-                timed("policy_step_kernel", lambda: fused.step(engine, oxy_i, o_count, t, seed, deterministic, h_t, h_t,
+                h_t, h_tc = none_if_zero(history(t)), none_if_zero(history(t, "critic"))
+                timed("policy_step_kernel", lambda: fused.step(engine, oxy_i, o_count, t, seed, deterministic, h_t, h_tc,
                                                                hist_a[t + D], hist_c[t + D], ha, hc, act[t], logp[t], v[t],
                                                                nets=("actor",) if actor_only else ("actor", "critic")))
                 if join is not None:
@@ -733,7 +743,7 @@ class MAPPO:
             if actor_only:
                 return self._train_batch(engine, arena, T, oxy, hist_a, hist_c, v, logp)
             engine.observe()
-            h_fin = none_if_zero([hist_c[T - 1 + D]] + history(T - 1)[:D - 1])
+            h_fin = none_if_zero(([hist_c[T - 1 + D]] + history(T - 1)[:D - 1]) if quirks else history(T, "critic"))
             scratch = torch.empty(B, N, E, **f32)
             fused.step(engine, oxy_i, o_count, T, seed, deterministic, h_fin, h_fin, scratch, scratch, ha, hc, None, None, v[T],
                        nets=("critic",))
@@ -763,7 +773,7 @@ class MAPPO:
         engine.observe()
         graph = ops.GraphBatch(engine.p_state.to(torch.float32), engine.e_state.to(torch.float32), oxy, engine.map_id,
                                o_count, engine.p_adj_bits, engine.e_adj, engine.o_adj_bits)
-        hist_final = [hist_c[T - 1 + D]] + history(T - 1)[:D - 1]
+        hist_final = ([hist_c[T - 1 + D]] + history(T - 1)[:D - 1]) if quirks else history(T, "critic")
         emb_c = enc.encode(graph, True, hist_final)
         feat_c, hc = self.critic.features(emb_c.view(1, B * N, E), hc)
         w, _ = self.critic.head_weight()
@@ -830,11 +840,13 @@ class MAPPO:
                 hc = torch.zeros(L, (hi - lo) * N, E, dtype=torch.float32, device=dev)
                 sl = slice(lo, hi)
 
-                def hist_of(t):
+                def hist_of(t, net="actor"):
                     out = []
                     for k in range(D):
-                        back = k // 2 + 1
-                        src = hist_c if k % 2 == 0 else hist_a
+                        if self.reference_quirks:      # the aliased list: C(t-1), A(t-1), C(t-2), ...
+                            back, src = k // 2 + 1, (hist_c if k % 2 == 0 else hist_a)
+                        else:                          # each network's own embeddings
+                            back, src = k + 1, (hist_a if net == "actor" else hist_c)
                         out.append(src[t - back + D][sl] if t - back >= 0 else None)
                     return out
 
@@ -853,9 +865,9 @@ class MAPPO:
                         join = torch.cuda.Event()
                         join.record(side)
                     timed("env_observe_kernel", st, lambda: engine.observe(lo=lo, hi=hi))
-                    h_t = hist_of(t)
+                    h_t, h_tc = hist_of(t), hist_of(t, "critic")
                     timed("policy_step_kernel", st, lambda: fused.step(
-                        view, oxy_i, o_count, t, seed, deterministic, h_t, h_t, hist_a[t + D][sl], hist_c[t + D][sl], ha, hc,
+                        view, oxy_i, o_count, t, seed, deterministic, h_t, h_tc, hist_a[t + D][sl], hist_c[t + D][sl], ha, hc,
                         act[t][sl], logp[t][sl], v[t][sl], row_offset=lo * N, tile_rows=full_tile,
                         debug=dbg[t, g] if dbg is not None else None))
                     if stagger > 0 and t == min(stagger, T - 1) - 1 and g + 1 < G:
@@ -865,7 +877,7 @@ class MAPPO:
                         st.wait_event(join)
                     timed("rollout_kernel", st, lambda: engine._closed_chunk(arena, rec_ptrs, lo, hi, t, 1, act[t:t + 1], 0, seed, st))
                 engine.observe(lo=lo, hi=hi)
-                h_fin = [hist_c[T - 1 + D][sl]] + hist_of(T - 1)[:D - 1]
+                h_fin = ([hist_c[T - 1 + D][sl]] + hist_of(T - 1)[:D - 1]) if self.reference_quirks else hist_of(T, "critic")
                 scratch = torch.empty(hi - lo, N, E, dtype=torch.float32, device=dev)
                 fused.step(view, oxy_i, o_count, T, seed, deterministic, h_fin, h_fin, scratch, scratch, ha, hc, None, None, v[T][sl],
                            nets=("critic",), row_offset=lo * N, tile_rows=full_tile)
@@ -904,8 +916,12 @@ class MAPPO:
     def _train_batch(self, engine, arena, T, oxy, hist_a, hist_c, v, logp):
         B, D, dev = engine.B, self.depth, self.device
         oxy_env = oxy[engine.map_id.long()].contiguous()
+        if self.reference_quirks:      # the critic's all-ones adjacency spans all O padded slots in training (:65,677): 76 phantom cells at (0,0)
+            o_count_train = torch.full((B,), engine.O, dtype=torch.int32, device=dev)
+        else:                          # ... or the map's real boundary cells, as in the rollout
+            o_count_train = torch.clamp(engine.boundary_count, max=engine.O)[engine.map_id.long()].to(torch.int32).contiguous()
         return TrainBatch(p=arena.p_state_f32[:T], e=arena.e_state_f32[:T, :, 0].contiguous(), oxy=oxy_env,
-                          o_count_train=torch.full((B,), engine.O, dtype=torch.int32, device=dev),
+                          o_count_train=o_count_train,
                           p_adj_bits=arena.p_adj_bits[:T], e_adj=arena.e_adj[:T], o_adj_bits=arena.o_adj_bits[:T],
                           hist_a=hist_a, hist_c=hist_c, v=v, a=arena.a_n[:T], logp=logp, r=arena.r[:T],
                           active=arena.active[:T], depth=D)

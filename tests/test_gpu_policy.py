@@ -548,3 +548,42 @@ def test_shuffled_minibatches_through_the_gather_kernel():
     reset_sn()
     _, tr2 = _train_grads(m, buf, steps, shuffle=True, shuffle_seed=11)
     assert sorted(tr2["permutation"].cpu().tolist()) == list(range(episodes))
+
+
+@pytest.mark.parametrize("depth", [1, 3])
+def test_reference_quirks_off_makes_rollout_and_training_forward_agree(depth):
+    """in the reference the rollout forward differs from the training forward at identical weights (the history list that
+    actor and critic alias during the rollout; the critic's all-ones obstacle adjacency over the 76 padded slots in training), so PPO
+    ratios are != 1 on the first epoch.  `MAPPO(..., reference_quirks=False)` is the self-consistent variant (never the parity
+    default): the training forward then reproduces the rollout's log-probs and values, and with the quirks on it does not."""
+    from distributed_multi_agent_reinforcement_learning_b200 import default_config
+    from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO
+    from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv, RolloutArena
+    B, N, T = 16, 8, 12
+    cfg = default_config(env__num_defender=N, env__max_steps=T, algo__depth=depth, algo__learner_device="cuda", algo__worker_device="cuda")
+    out = {}
+    for quirks in (False, True):
+        torch.manual_seed(7)
+        m = MAPPO(cfg, B, B // 2, "Learner", reference_quirks=quirks)
+        with torch.no_grad():
+            for p in m.ac_parameters:
+                if p.dim() == 1:
+                    p.add_(0.05 * torch.randn_like(p))
+        env = BatchedPursuitEnv(cfg, B, num_maps=4)
+        env.reset(seed=13)
+        arena = RolloutArena(env.params, B, T, env.device)
+        tb = m.rollout_batched(env, arena, T, seed=3)
+        if not quirks:                                        # the env-group pipelines give the same episode
+            snap_logp, snap_v = tb.logp.clone(), tb.v.clone()
+            env.reset(seed=13)
+            tb = m.rollout_batched(env, arena, T, seed=3, pipelines=2)
+            assert torch.equal(tb.logp, snap_logp) and torch.equal(tb.v, snap_v)
+        trace = {}
+        m.train(tb, B * T, return_numpy=False, trace=trace)
+        logp = torch.cat([t["logp"] for t in trace["mb"]], dim=1)
+        val = torch.cat([t["val"] for t in trace["mb"]], dim=1)
+        out[quirks] = (float((logp - tb.logp).abs().max()), float((val - tb.v[:-1]).abs().max()))
+        if not quirks:
+            torch.testing.assert_close(logp, tb.logp, rtol=1e-5, atol=2e-5)
+            torch.testing.assert_close(val, tb.v[:-1], rtol=1e-5, atol=2e-5)
+    assert out[True][0] > 1e-3 and out[True][1] > 1e-3, out      # the reference's behaviour: the two forwards disagree
