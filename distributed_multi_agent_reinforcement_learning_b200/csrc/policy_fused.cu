@@ -92,6 +92,7 @@ struct NetArgs {
     int sem_ld;
     const float *b_aggf[MAXD], *b_f[MAXD];
     const float *b_ih[2], *b_hh[2];
+    const float *b_comb[2];    // per GRU layer [4][E]: b_ir + b_hr, b_iz + b_hz, b_in, b_hn (pair kernel: 4 bias loads per cell group instead of 6)
     const float *head_b;
     const float *head_w_eff;   // critic: effective [E] row (fp32); actor: unused
     const float *hist[MAXD];   // [B,N,E] history embeddings, k = 0 most recent; null = zeros
@@ -1433,7 +1434,7 @@ __device__ void epi_cell_half_w(const Ctx &c, int l, int half, bool want_value, 
     constexpr int CG = WW / 4, CPH = 64 / CG;
     const NetArgs *na = c.na;
     const int row = 32 * (c.warp & 3) + c.lane, hh = c.warp >> 2;
-    const float *bi = na->b_ih[l], *bh = na->b_hh[l];
+    const float *bc = na->b_comb[l];
     const uint32_t taddr = c.tmem + ((uint32_t)(32 * (c.warp & 3)) << 16);
     int64_t gr;
     int env, i;
@@ -1465,19 +1466,17 @@ __device__ void epi_cell_half_w(const Ctx &c, int l, int half, bool want_value, 
         float hn[8];
 #pragma unroll
         for (int q4 = 0; q4 < 8; q4 += 4) {
-            const float4 bir = __ldg(reinterpret_cast<const float4 *>(bi + col + q4)), bhr = __ldg(reinterpret_cast<const float4 *>(bh + col + q4));
-            const float4 biz = __ldg(reinterpret_cast<const float4 *>(bi + E + col + q4)), bhz = __ldg(reinterpret_cast<const float4 *>(bh + E + col + q4));
-            const float4 bin = __ldg(reinterpret_cast<const float4 *>(bi + 2 * E + col + q4)), bhn = __ldg(reinterpret_cast<const float4 *>(bh + 2 * E + col + q4));
+            const float4 br = __ldg(reinterpret_cast<const float4 *>(bc + col + q4)), bz = __ldg(reinterpret_cast<const float4 *>(bc + E + col + q4));
+            const float4 bin = __ldg(reinterpret_cast<const float4 *>(bc + 2 * E + col + q4)), bhn = __ldg(reinterpret_cast<const float4 *>(bc + 3 * E + col + q4));
             float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (want_value) wv = __ldg(reinterpret_cast<const float4 *>(na->head_w_eff + col + q4));
-            const float f_bir[4] = {bir.x, bir.y, bir.z, bir.w}, f_bhr[4] = {bhr.x, bhr.y, bhr.z, bhr.w};
-            const float f_biz[4] = {biz.x, biz.y, biz.z, biz.w}, f_bhz[4] = {bhz.x, bhz.y, bhz.z, bhz.w};
+            const float f_br[4] = {br.x, br.y, br.z, br.w}, f_bz[4] = {bz.x, bz.y, bz.z, bz.w};
             const float f_bin[4] = {bin.x, bin.y, bin.z, bin.w}, f_bhn[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
             const float f_w[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float r = fast_sigmoid((__uint_as_float(ar[q4 + q]) + f_bir[q]) + f_bhr[q]);
-                const float z = fast_sigmoid((__uint_as_float(az[q4 + q]) + f_biz[q]) + f_bhz[q]);
+                const float r = fast_sigmoid(__uint_as_float(ar[q4 + q]) + f_br[q]);
+                const float z = fast_sigmoid(__uint_as_float(az[q4 + q]) + f_bz[q]);
                 const float n = fast_tanh((__uint_as_float(an[q4 + q]) + f_bin[q]) + r * (__uint_as_float(ahn[q4 + q]) + f_bhn[q]));
                 hn[q4 + q] = (1.f - z) * n + z * hp[q4 + q];
                 vdot = fmaf(f_w[q], hn[q4 + q], vdot);
@@ -1814,6 +1813,17 @@ pack_unit_kernel(const float *__restrict__ W, int64_t ld, int rows_valid, int n_
     *reinterpret_cast<unsigned short *>(out + off + plane) = (unsigned short)(lo & 0xffffu);
 }
 
+// b_ir + b_hr, b_iz + b_hz, b_in, b_hn of one GRU layer -> out [4][E]
+__global__ void __launch_bounds__(128)
+combine_gru_bias_kernel(const float *__restrict__ b_ih, const float *__restrict__ b_hh, float *__restrict__ out)
+{
+    const int c = threadIdx.x;
+    out[c] = b_ih[c] + b_hh[c];
+    out[E + c] = b_ih[E + c] + b_hh[E + c];
+    out[2 * E + c] = b_ih[2 * E + c];
+    out[3 * E + c] = b_hh[2 * E + c];
+}
+
 struct UnitSrc {
     const float *W;
     int64_t ld;
@@ -1921,7 +1931,7 @@ using namespace marl;
 extern "C" int64_t marl_policy_pack_bytes(int32_t depth, int32_t is_actor)
 {
     if (depth < 1 || depth > pf::MAXD) return -1;
-    return 3 * pf::layout_bytes(depth, is_actor);        // the kernel variants' images: [one chain per CTA][two CTAs per SM][pair]
+    return 3 * pf::layout_bytes(depth, is_actor) + 2 * 4 * pf::E * (int64_t)sizeof(float);   // [one chain per CTA][two CTAs per SM][pair][combined GRU biases]
 }
 
 extern "C" int marl_policy_pack(const marl_dhgn_weights *w, int32_t depth, int32_t is_actor, int32_t action_dim, void *d_packed,
@@ -1942,6 +1952,11 @@ extern "C" int marl_policy_pack(const marl_dhgn_weights *w, int32_t depth, int32
             if (rc) return rc;
             out += pf::unit_bytes(us[u].n_out);
         }
+    }
+    for (int l = 0; l < 2; ++l) {
+        pf::combine_gru_bias_kernel<<<1, pf::E, 0, (cudaStream_t)stream>>>(w->gru_b_ih[l], w->gru_b_hh[l], reinterpret_cast<float *>(out) + l * 4 * pf::E);
+        rc = check_launch("combine_gru_bias_kernel");
+        if (rc) return rc;
     }
     return MARL_OK;
 }
@@ -1967,7 +1982,10 @@ static int fill_net(pf::NetArgs &na, const marl_dhgn_weights *w, const marl_poli
         na.b_f[k] = k < depth ? w->fcra_b[k] : nullptr;
         na.hist[k] = k < depth ? io->d_hist[k] : nullptr;
     }
-    for (int l = 0; l < 2; ++l) { na.b_ih[l] = w->gru_b_ih[l]; na.b_hh[l] = w->gru_b_hh[l]; }
+    for (int l = 0; l < 2; ++l) {
+        na.b_ih[l] = w->gru_b_ih[l]; na.b_hh[l] = w->gru_b_hh[l];
+        na.b_comb[l] = reinterpret_cast<const float *>(static_cast<const unsigned char *>(io->d_packed) + 3 * pf::layout_bytes(depth, is_actor)) + l * 4 * pf::E;
+    }
     na.head_b = w->head_b;
     na.head_w_eff = is_actor ? nullptr : w->head_w;
     na.emb_out = io->d_emb_out;
