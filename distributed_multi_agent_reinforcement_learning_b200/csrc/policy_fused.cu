@@ -1798,12 +1798,15 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
 
 // ---- weight packing: one unit = W[rows, k0 : k0+128] -> 2 k-blocks (K = 64) x (hi plane, lo plane) in the smem image ------------
 __global__ void __launch_bounds__(256)
-pack_unit_kernel(const float *__restrict__ W, int64_t ld, int rows_valid, int n_out, int k0, unsigned char *__restrict__ out)
+pack_unit_kernel(const float *__restrict__ W, int64_t ld, int rows_valid, int n_out, int k0, int split, int jump,
+                 unsigned char *__restrict__ out)
 {
     const int idx = blockIdx.x * 256 + threadIdx.x;      // (n, k)
     if (idx >= n_out * 128) return;
     const int n = idx >> 7, k = idx & 127;
-    const float v = n < rows_valid ? W[(int64_t)n * ld + k0 + k] : 0.f;
+    // unit rows >= split come from `jump` source rows further down (two 64-row halves of different GRU gates in one 128-row unit)
+    const int src = n + (n >= split ? jump : 0);
+    const float v = n < rows_valid ? W[(int64_t)src * ld + k0 + k] : 0.f;
     uint32_t hi, lo;
     split_h2(v, 0.f, hi, lo);
     const int kb = k >> 6, kk = k & 63;
@@ -1828,6 +1831,7 @@ struct UnitSrc {
     const float *W;
     int64_t ld;
     int rows, n_out, k0, acc_col, accumulate, last;
+    int split = 1 << 30, jump = 0;      // see pack_unit_kernel
 };
 
 static int build_units(const marl_dhgn_weights *w, int depth, int is_actor, int A, UnitSrc *us, int mode /* 0 one chain per CTA, 1 two CTAs per SM, 2 pair */)
@@ -1835,6 +1839,12 @@ static int build_units(const marl_dhgn_weights *w, int depth, int is_actor, int 
     int n = 0;
     auto add = [&](const float *W, int64_t ld, int rows, int n_out, int k0, int acc, int accu, int last) {
         us[n++] = UnitSrc{W, ld, rows, n_out, k0, acc, accu, last};
+    };
+    auto add_rz = [&](const float *W, int acc, int accu) {      // rows [0,64) of gate r and of gate z of one half: one 128-row unit
+        UnitSrc u{W, E, E, E, 0, acc, accu, 0};
+        u.split = 64;
+        u.jump = E - 64;
+        us[n++] = u;
     };
     for (int r = 0; r < 3; ++r) {
         add(w->agg_v_w, E, E, E, 0, 0, 0, 1);
@@ -1850,11 +1860,13 @@ static int build_units(const marl_dhgn_weights *w, int depth, int is_actor, int 
             // pair kernel: 64-column halves, accumulators r @0, z @64, n_i @128, n_h @192, in the order
             // W_ih(half 0) | W_hh(half 0) | W_hh(half 1) | W_ih(half 1): X holds x, h_prev, h_prev, x (one re-staging of each)
             const float *wi = w->gru_w_ih[l], *wh = w->gru_w_hh[l];
-            const int64_t ro = (int64_t)64 * E, g1 = (int64_t)E * E, g2 = (int64_t)2 * E * E;
-            add(wi, E, 64, 64, 0, 0, 0, 0); add(wi + g1, E, 64, 64, 0, 64, 0, 0); add(wi + g2, E, 64, 64, 0, 128, 0, 1);
-            add(wh, E, 64, 64, 0, 0, 1, 0); add(wh + g1, E, 64, 64, 0, 64, 1, 0); add(wh + g2, E, 64, 64, 0, 192, 0, 1);
-            add(wh + ro, E, 64, 64, 0, 0, 0, 0); add(wh + g1 + ro, E, 64, 64, 0, 64, 0, 0); add(wh + g2 + ro, E, 64, 64, 0, 192, 0, 1);
-            add(wi + ro, E, 64, 64, 0, 0, 1, 0); add(wi + g1 + ro, E, 64, 64, 0, 64, 1, 0); add(wi + g2 + ro, E, 64, 64, 0, 128, 0, 1);
+            const int64_t ro = (int64_t)64 * E, g2 = (int64_t)2 * E * E;
+            // the r and z rows of a half form ONE 128-row unit (accumulator columns r @0, z @64 are adjacent): 8 units per layer instead
+            // of 12, and the A tile is read from shared memory twice per group instead of three times
+            add_rz(wi, 0, 0); add(wi + g2, E, 64, 64, 0, 128, 0, 1);
+            add_rz(wh, 0, 1); add(wh + g2, E, 64, 64, 0, 192, 0, 1);
+            add_rz(wh + ro, 0, 0); add(wh + g2 + ro, E, 64, 64, 0, 192, 0, 1);
+            add_rz(wi + ro, 0, 1); add(wi + g2 + ro, E, 64, 64, 0, 128, 0, 1);
         } else if (mode == 0) {
             for (int g = 0; g < 3; ++g) add(w->gru_w_ih[l] + (int64_t)g * E * E, E, E, E, 0, 128 * g, 0, g == 2);
             add(w->gru_w_hh[l], E, E, E, 0, 0, 1, 0);
@@ -1947,7 +1959,7 @@ extern "C" int marl_policy_pack(const marl_dhgn_weights *w, int32_t depth, int32
         const int n = pf::build_units(w, depth, is_actor, action_dim, us, mode);
         for (int u = 0; u < n; ++u) {
             const int total = us[u].n_out * 128;
-            pf::pack_unit_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(us[u].W, us[u].ld, us[u].rows, us[u].n_out, us[u].k0, out);
+            pf::pack_unit_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(us[u].W, us[u].ld, us[u].rows, us[u].n_out, us[u].k0, us[u].split, us[u].jump, out);
             rc = check_launch("pack_unit_kernel");
             if (rc) return rc;
             out += pf::unit_bytes(us[u].n_out);

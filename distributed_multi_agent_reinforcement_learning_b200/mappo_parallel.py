@@ -803,6 +803,8 @@ class MAPPO:
         rec_ptrs = arena.record_pointers()
         diff = int(engine.params.difficulty)
         full_tile = (128 // N) * N if N <= 128 else 0      # concurrent launches: full tiles, SMs left over for the neighbours
+        if os.environ.get("MARL_PIPE_TILE_ROWS"):            # tuning knob for tools/
+            full_tile = int(os.environ["MARL_PIPE_TILE_ROWS"])
         fork = torch.cuda.Event(enable_timing=timers is not None)
         fork.record(main)
         if timers is not None:
