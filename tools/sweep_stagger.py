@@ -6,6 +6,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import ab  # noqa: E402,F401  (MARL_AB_LIB=<alternative libmarl_b200.so> for A/B runs)
 import bench  # noqa: E402
 from distributed_multi_agent_reinforcement_learning_b200.mappo_parallel import MAPPO, RolloutGraph  # noqa: E402
 from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv, RolloutArena  # noqa: E402
