@@ -1375,12 +1375,11 @@ __device__ void phase_msg_pair01(const Ctx &c, unsigned char *XA, unsigned char 
         const float4 ev = c.s_e[r0 / NA];
         if (rel == 0) {
             float qj[NA][4];
-            float4 pj[NA];
 #pragma unroll
             for (int j = 0; j < NA; ++j) {
-                pj[j] = c.s_p[r0 + j];
+                const float4 pj = c.s_p[r0 + j];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) qj[j][q] = fmaf(w[q][3], pj[j].w, fmaf(w[q][2], pj[j].z, fmaf(w[q][1], pj[j].y, w[q][0] * pj[j].x)));
+                for (int q = 0; q < 4; ++q) qj[j][q] = fmaf(w[q][3], pj.w, fmaf(w[q][2], pj.z, fmaf(w[q][1], pj.y, w[q][0] * pj.x)));
             }
             const uint32_t my_word = lane < NA ? a->p_adj[(gr0 + lane) * a->NW] : 0u;
             const float nrm_c = 1.f / fmaxf((float)NA, 1e-12f);
@@ -1388,7 +1387,8 @@ __device__ void phase_msg_pair01(const Ctx &c, unsigned char *XA, unsigned char 
             for (int i = 0; i < NA; ++i) {
                 const uint32_t word = __shfl_sync(0xffffffffu, my_word, i);
                 const int cnt = __popc(word & ((1u << NA) - 1u));
-                const float dex = pj[i].x - ev.x, dey = pj[i].y - ev.y, dez = pj[i].z - ev.z, dew = pj[i].w - ev.w;
+                const float4 pi = c.s_p[r0 + i];               // (re-read: keeping all NA states live costs 32 registers in the hottest loop)
+                const float dex = pi.x - ev.x, dey = pi.y - ev.y, dez = pi.z - ev.z, dew = pi.w - ev.w;
                 float ai[4], acc_a[4], acc_c[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -1492,7 +1492,7 @@ __device__ void epi_cell_half_w(const Ctx &c, int l, int half, bool want_value, 
 
 // Launched with WW + 4 warps: the worker warps (whole warpgroups) take the registers that the loader / issuer warpgroup (two working
 // lanes, two idle warps) gives back with setmaxnreg, so the SIMT phases get 112 registers per thread instead of 96.
-constexpr int PAIR_WORKER_REGS = 104, PAIR_OTHER_REGS = 56;   // the CTA owns 640 x 96 registers: 512 x 104 + 128 x 56 fits; the issuer lane needs ~50
+constexpr int PAIR_WORKER_REGS = 112, PAIR_OTHER_REGS = 32;   // the CTA owns 640 x 96 registers: 512 x 104 + 128 x 56 fits; the issuer lane needs ~50
 // PROF: per-phase cycle counters in registers (tools/fused_phase_profile.py, MARL_POLICY_PROFILE=1); the production instantiation
 // only writes the CTA's start / end %globaltimer, SM id and total cycles when a debug buffer is given, and keeps nothing live for it.
 #define PP_TICK(slot) do { if constexpr (PROF) { const long long now_ = clock64(); tk[slot] += now_ - t_prev; \
@@ -1627,11 +1627,24 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
                     }
                     PP_TICK(0);
                 } else if (is_fcra_fill) {
-                    float4 pre[Lay<WW>::RPW];
-                    uint32_t words[4] = {0u, 0u, 0u, 0u};
-                    phase_fcra_prefetch<WW>(c, fk, pre, words);
-                    wait_prev();
-                    phase_fcra_finish<WW>(c, fk, pre, words);
+                    // (one straight-line block per env size: through the size-dispatching wrappers the row array ended up on the
+                    // stack - the loads were stored to local memory before the wait and read back after it)
+                    if (pair01 && a.O <= OXY_CAP && a.N == 8) {
+                        float4 pre[Lay<WW>::RPW];
+                        uint32_t words[4] = {0u, 0u, 0u, 0u};
+                        fcra_prefetch<8, WW>(c, fk, pre, words);
+                        wait_prev();
+                        fcra_finish<8, WW>(c, pre, words);
+                    } else if (pair01 && a.O <= OXY_CAP && a.N == 4) {
+                        float4 pre[Lay<WW>::RPW];
+                        uint32_t words[4] = {0u, 0u, 0u, 0u};
+                        fcra_prefetch<4, WW>(c, fk, pre, words);
+                        wait_prev();
+                        fcra_finish<4, WW>(c, pre, words);
+                    } else {
+                        wait_prev();
+                        phase_fcra_generic<WW>(c, fk);
+                    }
                     PP_TICK(2);
                 } else if (s < G0 + 8) {
                     const int l = (s - G0) >> 2, gsub = (s - G0) & 3;
