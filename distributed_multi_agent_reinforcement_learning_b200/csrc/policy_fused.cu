@@ -473,15 +473,13 @@ __device__ void phase_msg_generic(const Ctx &c, int rel)
 //               cc_i = W2 p_i + b2, u_k = W2[:, :2] o_k                    (2 instructions per (i, k, channel));
 //   the map's boundary cells live in registers (lane l holds cells l, l+32, ...) and are broadcast with shuffles.
 template <int NA, int WW>
-__device__ void phase_msg_fast(const Ctx &c, int rel)
+__device__ void phase_msg_fast(const Ctx &c, int rel, const float (&w)[4][8], const float (&b)[4])
 {
     constexpr int RPW = Lay<WW>::RPW;
     static_assert(RPW % NA == 0, "whole envs per warp");
     const StepArgs *a = c.a;
     const NetArgs *na = c.na;
     const int lane = c.lane;
-    float w[4][8], b[4];
-    load_msg_weights(na, rel, lane, w, b);
     constexpr int RC = NA < 8 ? NA : 8;      // rows per register chunk of the critic's obstacle relation
 #pragma unroll 1
     for (int g = 0; g < RPW / NA; ++g) {
@@ -497,12 +495,11 @@ __device__ void phase_msg_fast(const Ctx &c, int rel)
         const float4 ev = c.s_e[r0 / NA];
         if (rel == 0) {
             float qj[NA][4];
-            float4 pj[NA];
 #pragma unroll
             for (int j = 0; j < NA; ++j) {
-                pj[j] = c.s_p[r0 + j];
+                const float4 pj = c.s_p[r0 + j];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) qj[j][q] = fmaf(w[q][3], pj[j].w, fmaf(w[q][2], pj[j].z, fmaf(w[q][1], pj[j].y, w[q][0] * pj[j].x)));
+                for (int q = 0; q < 4; ++q) qj[j][q] = fmaf(w[q][3], pj.w, fmaf(w[q][2], pj.z, fmaf(w[q][1], pj.y, w[q][0] * pj.x)));
             }
 #pragma unroll
             const uint32_t my_word = (!na->all_ones && lane < NA) ? a->p_adj[(gr0 + lane) * a->NW] : 0xffffffffu;
@@ -510,7 +507,8 @@ __device__ void phase_msg_fast(const Ctx &c, int rel)
             for (int i = 0; i < NA; ++i) {
                 const uint32_t word = __shfl_sync(0xffffffffu, my_word, i);
                 const int cnt = __popc(word & ((NA == 32) ? 0xffffffffu : ((1u << NA) - 1u)));
-                const float dex = pj[i].x - ev.x, dey = pj[i].y - ev.y, dez = pj[i].z - ev.z, dew = pj[i].w - ev.w;
+                const float4 pi = c.s_p[r0 + i];               // (re-read: keeping all NA states live costs 4 NA registers in the hottest loop)
+                const float dex = pi.x - ev.x, dey = pi.y - ev.y, dez = pi.z - ev.z, dew = pi.w - ev.w;
                 float ai[4], acc[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -649,6 +647,14 @@ __device__ void phase_msg_fast(const Ctx &c, int rel)
             }
         }
     }
+}
+
+template <int NA, int WW>
+__device__ void phase_msg_fast(const Ctx &c, int rel)
+{
+    float w[4][8], b[4];
+    load_msg_weights(c.na, rel, c.lane, w, b);
+    phase_msg_fast<NA, WW>(c, rel, w, b);
 }
 
 template <int WW>
@@ -1350,14 +1356,12 @@ struct RingCursor {
 // ---- relations 0 and 1 for BOTH chains at once (env-grouped fast path, N = NA in {4, 8}): same arithmetic, term for term, as
 // phase_msg_fast run once per network - the pair terms / the evader message are simply not computed twice
 template <int NA, int WW>
-__device__ void phase_msg_pair01(const Ctx &c, unsigned char *XA, unsigned char *XC, int rel)
+__device__ void phase_msg_pair01(const Ctx &c, unsigned char *XA, unsigned char *XC, int rel, const float (&w)[4][8], const float (&b)[4])
 {
     constexpr int RPW = Lay<WW>::RPW;
     static_assert(RPW % NA == 0, "whole envs per warp");
     const StepArgs *a = c.a;
     const int lane = c.lane;
-    float w[4][8], b[4];
-    load_msg_weights(c.na, rel, lane, w, b);
 #pragma unroll 1
     for (int g = 0; g < RPW / NA; ++g) {
         const int r0 = RPW * c.warp + g * NA;
@@ -1495,10 +1499,7 @@ __device__ void epi_cell_half_w(const Ctx &c, int l, int half, bool want_value, 
 constexpr int PAIR_WORKER_REGS = 112, PAIR_OTHER_REGS = 32;   // the CTA owns 640 x 96 registers: 512 x 104 + 128 x 56 fits; the issuer lane needs ~50
 // PROF: per-phase cycle counters in registers (tools/fused_phase_profile.py, MARL_POLICY_PROFILE=1); the production instantiation
 // only writes the CTA's start / end %globaltimer, SM id and total cycles when a debug buffer is given, and keeps nothing live for it.
-#define PP_TICK(slot) do { if constexpr (PROF) { const long long now_ = clock64(); tk[slot] += now_ - t_prev; \
-    if (a.dbg && threadIdx.x == 0 && pp_s < 32) { const int kind_ = (slot) == 9 ? 0 : ((slot) == 11 ? 1 : ((slot) == 10 ? 3 : 2)); \
-        a.dbg[((size_t)gridDim.x + 16 * blockIdx.x + 4 * kind_) * 16 + 2 * pp_s + pp_ch] += now_ - t_prev; } \
-    t_prev = now_; } } while (0)
+#define PP_TICK(slot) do { if constexpr (PROF) { const long long now_ = clock64(); tk[slot] += now_ - t_prev; t_prev = now_; } } while (0)
 template <int WW, bool PROF>
 __global__ void __launch_bounds__((WW + 4) * 32, 1)
 policy_pair_kernel(const __grid_constant__ StepArgs a)
@@ -1579,8 +1580,6 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
                 if (s >= (ch == 0 ? S_ACTOR : S_CRITIC)) continue;
-                const int pp_s = s, pp_ch = ch;
-                (void)pp_s; (void)pp_ch;
                 const bool shared = pair01 && (s == 0 || s == 2);
                 if (shared && ch == 1) continue;               // done together with the actor's
                 const NetArgs *na = &a.net[ch];
@@ -1617,12 +1616,22 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
                     wait_prev();
                     epi_store<WW>(c, acc_col, bias, relu, wp, na->sem_ld, gout);
                     PP_TICK(1);
-                } else if (is_msg) {
-                    wait_prev();
-                    if (shared) {                              // messages of relation s/2 -> X
-                        if (a.N == 8) phase_msg_pair01<8, WW>(c, smem, smem + M::XC_OFF, s >> 1);
-                        else phase_msg_pair01<4, WW>(c, smem, smem + M::XC_OFF, s >> 1);
+                } else if (is_msg) {                           // messages of relation s/2 -> X
+                    if (pair01 && a.O <= OXY_CAP) {
+                        // the layer's weights are fetched before the wait for the running MMA group (their L2 latency, ~700 cycles at
+                        // the head of every message phase, passes meanwhile); straight-line per env size, so they stay in registers
+                        float w[4][8], b[4];
+                        load_msg_weights(na, s >> 1, lane, w, b);
+                        wait_prev();
+                        if (a.N == 8) {
+                            if (shared) phase_msg_pair01<8, WW>(c, smem, smem + M::XC_OFF, s >> 1, w, b);
+                            else phase_msg_fast<8, WW>(c, s >> 1, w, b);
+                        } else {
+                            if (shared) phase_msg_pair01<4, WW>(c, smem, smem + M::XC_OFF, s >> 1, w, b);
+                            else phase_msg_fast<4, WW>(c, s >> 1, w, b);
+                        }
                     } else {
+                        wait_prev();
                         phase_msg<WW>(c, s >> 1);
                     }
                     PP_TICK(0);

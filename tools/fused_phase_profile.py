@@ -62,9 +62,6 @@ for s_ in np.unique(sm[ok]):
 print(f"gap between consecutive CTAs on an SM: median {np.median(gaps) / 1e3:.2f} us, max {np.max(gaps) / 1e3:.2f} us; CTAs per SM: {ok.sum() / len(np.unique(sm[ok])):.2f}")
 if int(os.environ.get("MARL_VARIANT", "0")) == 3:
     grid = len(d)                                 # CTA rows carry a %globaltimer stamp; the per-step rows follow them
-    steps = d_all[grid:grid + 16 * grid].reshape(grid, 4, 64).mean(axis=0).reshape(4, 32, 2) / 3.0      # three launches accumulate
-    for kind, nm in enumerate(("pre/loop", "wait", "work", "signal")):
-        print(f"per-step {nm:9s} (actor/critic):", " ".join(f"{int(x)}/{int(y)}" for x, y in steps[kind][:20]))
     d = d[:grid]
     tot = d[:, 12]
     print(f"pair items {len(d)}; per-item worker cycles: mean {tot.mean():.0f} min {tot.min():.0f} max {tot.max():.0f}; sum/148 = {tot.sum() / 148:.0f}")
