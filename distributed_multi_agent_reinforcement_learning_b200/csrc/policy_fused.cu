@@ -1582,6 +1582,7 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
                 if (s >= (ch == 0 ? S_ACTOR : S_CRITIC)) continue;
                 const bool shared = pair01 && (s == 0 || s == 2);
                 if (shared && ch == 1) continue;               // done together with the actor's
+                PP_TICK(8);
                 const NetArgs *na = &a.net[ch];
                 c.na = na;
                 c.X = smem + ch * M::XC_OFF;
@@ -1720,6 +1721,7 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
             if constexpr (PROF) {
                 for (int q = 0; q < 6; ++q) d[q] = tk[q];
                 d[9] = tk[9]; d[10] = tk[10]; d[11] = tk[11];
+                d[15] = tk[8];       // (PROF only: the SM id slot carries the loop-overhead counter)
             }
         }
     } else if (warp == WW) {

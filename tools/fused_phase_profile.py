@@ -65,7 +65,7 @@ if int(os.environ.get("MARL_VARIANT", "0")) == 3:
     d = d[:grid]
     tot = d[:, 12]
     print(f"pair items {len(d)}; per-item worker cycles: mean {tot.mean():.0f} min {tot.min():.0f} max {tot.max():.0f}; sum/148 = {tot.sum() / 148:.0f}")
-    for i, n in ((0, "messages"), (1, "epi_store"), (2, "fcra"), (3, "fill_x"), (4, "cell halves"), (5, "head"), (9, "loop+prefetch"), (10, "signal"), (11, "wait mma")):
+    for i, n in ((0, "messages"), (1, "epi_store"), (2, "fcra"), (3, "fill_x"), (4, "cell halves"), (5, "head"), (15, "loop back-edge"), (9, "dispatch+prefetch"), (10, "signal"), (11, "wait mma")):
         print(f"   {n:14s} {d[:, i].mean():10.0f} cycles ({100 * d[:, i].mean() / tot.mean():5.1f}%)")
     print(f"   issuer: waiting for the workers {d[:, 6].mean():.0f}, for weights {d[:, 7].mean():.0f}, total {d[:, 8].mean():.0f} -> issuing / idle in MMA queue {d[:, 8].mean() - d[:, 6].mean() - d[:, 7].mean():.0f}")
     sys.exit(0)
