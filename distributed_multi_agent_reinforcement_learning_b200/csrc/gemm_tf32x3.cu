@@ -88,6 +88,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t
         "}\n" ::"r"(tmem_c), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one_lane()      // see tc_common.cuh: elect_one
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -222,25 +234,29 @@ gemm_tf32x3_kernel(Args a)
                 }
             }
         }
-    } else if (lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % STAGES, round = kb / STAGES;
             mbar_wait(smem_u32(&bars[s]), round & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+            if (elect_one_lane()) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 8; ++kk) {
-                const uint64_t a_hi = make_desc(base + kk * 32), a_lo = make_desc(base + TILE_BYTES + kk * 32);
-                const uint64_t b_hi = make_desc(base + 2 * TILE_BYTES + kk * 32), b_lo = make_desc(base + 3 * TILE_BYTES + kk * 32);
-                // main accumulator kb&1 (columns 0 / 128), corrections in columns 256..383
-                umma_tf32(tmem_base + (uint32_t)(kb & 1) * BN, a_hi, b_hi, (kb >= 2 || kk) ? 1u : 0u);
-                umma_tf32(tmem_base + 2 * BN, a_lo, b_hi, (kb | kk) ? 1u : 0u);
-                umma_tf32(tmem_base + 2 * BN, a_hi, b_lo, 1u);
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                    const uint64_t a_hi = make_desc(base + kk * 32), a_lo = make_desc(base + TILE_BYTES + kk * 32);
+                    const uint64_t b_hi = make_desc(base + 2 * TILE_BYTES + kk * 32), b_lo = make_desc(base + 3 * TILE_BYTES + kk * 32);
+                    // main accumulator kb&1 (columns 0 / 128), corrections in columns 256..383
+                    umma_tf32(tmem_base + (uint32_t)(kb & 1) * BN, a_hi, b_hi, (kb >= 2 || kk) ? 1u : 0u);
+                    umma_tf32(tmem_base + 2 * BN, a_lo, b_hi, (kb | kk) ? 1u : 0u);
+                    umma_tf32(tmem_base + 2 * BN, a_hi, b_lo, 1u);
+                }
+                umma_commit(smem_u32(&bars[STAGES + s]));     // frees this smem stage once the MMAs have read it
             }
-            umma_commit(smem_u32(&bars[STAGES + s]));         // frees this smem stage once the MMAs have read it
+            __syncwarp();
         }
-        umma_commit(smem_u32(&bars[2 * STAGES]));             // accumulator complete -> epilogue
+        if (elect_one_lane()) umma_commit(smem_u32(&bars[2 * STAGES]));   // accumulator complete -> epilogue
+        __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

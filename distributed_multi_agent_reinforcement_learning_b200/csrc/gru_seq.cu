@@ -110,17 +110,21 @@ __device__ __forceinline__ void issuer_loop(int T, unsigned char *X, unsigned ch
                 fence_after();
                 const uint32_t wa = smem_u32(Wst + s * WSTAGE), xb = smem_u32(Xg + kb * Tile<NR>::KB);
                 const uint64_t a_hi0 = make_desc(wa), a_lo0 = make_desc(wa + WPLANE), b_hi0 = make_desc(xb), b_lo0 = make_desc(xb + Tile<NR>::PLANE);
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const uint32_t accum = (BWD ? (g | kb | kk) : (kb | kk)) ? 1u : 0u;
-                    umma_tf32(acc, a_hi0 + 2 * kk, b_hi0 + 2 * kk, idesc, accum);
-                    umma_tf32(corr, a_lo0 + 2 * kk, b_hi0 + 2 * kk, idesc, accum);
-                    umma_tf32(corr, a_hi0 + 2 * kk, b_lo0 + 2 * kk, idesc, 1u);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t accum = (BWD ? (g | kb | kk) : (kb | kk)) ? 1u : 0u;
+                        umma_tf32(acc, a_hi0 + 2 * kk, b_hi0 + 2 * kk, idesc, accum);
+                        umma_tf32(corr, a_lo0 + 2 * kk, b_hi0 + 2 * kk, idesc, accum);
+                        umma_tf32(corr, a_hi0 + 2 * kk, b_lo0 + 2 * kk, idesc, 1u);
+                    }
+                    umma_commit(smem_u32(&bars[NSTAGE + s]));
                 }
-                umma_commit(smem_u32(&bars[NSTAGE + s]));
+                __syncwarp();
             }
         }
-        umma_commit(smem_u32(&bars[MMA_DONE]));
+        if (elect_one()) umma_commit(smem_u32(&bars[MMA_DONE]));
+        __syncwarp();
     }
 }
 
@@ -236,7 +240,7 @@ gru_seq_fwd_kernel(const __grid_constant__ FwdArgs a)
     } else if (warp == 8) {
         if (lane == 0) loader_loop<NSTAGE>(a.packed, a.T, Wst, bars);
     } else {
-        if (lane == 0) issuer_loop<NR, false, NSTAGE>(a.T, X, Wst, bars, tmem_base);
+        issuer_loop<NR, false, NSTAGE>(a.T, X, Wst, bars, tmem_base);      // whole warp, elected lane issues
     }
     fence_before();
     __syncthreads();
@@ -344,7 +348,7 @@ gru_seq_bwd_kernel(const __grid_constant__ BwdArgs a)
     } else if (warp == 8) {
         if (lane == 0) loader_loop<NSTAGE>(a.packed, a.T, Wst, bars);
     } else {
-        if (lane == 0) issuer_loop<NR, true, NSTAGE>(a.T, X, Wst, bars, tmem_base);
+        issuer_loop<NR, true, NSTAGE>(a.T, X, Wst, bars, tmem_base);       // whole warp, elected lane issues
     }
     fence_before();
     __syncthreads();

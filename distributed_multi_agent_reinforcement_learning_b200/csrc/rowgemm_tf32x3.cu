@@ -184,8 +184,8 @@ rowgemm_kernel(const __grid_constant__ Args a)
                     }
         }
     } else {
-        // ================================================================================= MMA issuer
-        if (lane == 0) {
+        // ================================================================================= MMA issuer (whole warp, elected lane issues)
+        {
             const uint32_t idesc = idesc_tf32(128, 128);
             int it = 0, group = 0;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
@@ -205,17 +205,21 @@ rowgemm_kernel(const __grid_constant__ Args a)
                             fence_after();
                             const uint32_t xa = smem_u32(X + kb * XKB), wb = smem_u32(Wst + s * WSTAGE);
                             const uint64_t a_hi0 = make_desc(xa), a_lo0 = make_desc(xa + TILE), b_hi0 = make_desc(wb), b_lo0 = make_desc(wb + TILE);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                const uint32_t first = (kc | kb | kk) ? 1u : 0u;
-                                umma_tf32(acc, a_hi0 + 2 * kk, b_hi0 + 2 * kk, idesc, first);
-                                umma_tf32(corr, a_lo0 + 2 * kk, b_hi0 + 2 * kk, idesc, split_corr ? first : 1u);
-                                umma_tf32(corr, a_hi0 + 2 * kk, b_lo0 + 2 * kk, idesc, 1u);
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    const uint32_t first = (kc | kb | kk) ? 1u : 0u;
+                                    umma_tf32(acc, a_hi0 + 2 * kk, b_hi0 + 2 * kk, idesc, first);
+                                    umma_tf32(corr, a_lo0 + 2 * kk, b_hi0 + 2 * kk, idesc, split_corr ? first : 1u);
+                                    umma_tf32(corr, a_hi0 + 2 * kk, b_lo0 + 2 * kk, idesc, 1u);
+                                }
+                                umma_commit(smem_u32(&bars[NSTAGE + s]));
                             }
-                            umma_commit(smem_u32(&bars[NSTAGE + s]));
+                            __syncwarp();
                         }
                     }
-                    umma_commit(smem_u32(&bars[BAR_MMA_DONE]));
+                    if (elect_one()) umma_commit(smem_u32(&bars[BAR_MMA_DONE]));
+                    __syncwarp();
                     ++group;
                 }
         }

@@ -57,6 +57,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t
         "}\n" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a converged warp (elect.sync).  MMA issuers run their loop on the WHOLE warp (warp-uniform control flow, every lane
+// polls the barriers) and issue from the elected lane: under `if (lane == 0)` ptxas has to wrap every tcgen05.mma in a lane-serialising
+// loop to get its operands into uniform registers (~20 instructions per MMA, with local-memory traffic) - several times the duration
+// of a small MMA.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -169,8 +169,8 @@ wgrad_kernel(const __grid_constant__ Args a)
                 a.bias_partial[(size_t)slice * (gridDim.x / a.n_tiles_k) * 128 + (size_t)(tile / a.n_tiles_k) * 128 + threadIdx.x] = v;
             }
         }
-    } else if (lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
         const uint32_t idesc = idesc_tf32(128, 128);
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % STAGES, round = kb / STAGES;
@@ -179,15 +179,19 @@ wgrad_kernel(const __grid_constant__ Args a)
             const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
             const uint64_t a_hi0 = make_desc(base), a_lo0 = make_desc(base + PLANE), b_hi0 = make_desc(base + 2 * PLANE), b_lo0 = make_desc(base + 3 * PLANE);
             const uint32_t main_acc = tmem_base + (uint32_t)(kb & 1) * 128u, corr = tmem_base + 256u;
+            if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 8; ++kk) {
-                umma_tf32(main_acc, a_hi0 + 2 * kk, b_hi0 + 2 * kk, idesc, (kb >= 2 || kk) ? 1u : 0u);
-                umma_tf32(corr, a_lo0 + 2 * kk, b_hi0 + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
-                umma_tf32(corr, a_hi0 + 2 * kk, b_lo0 + 2 * kk, idesc, 1u);
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                    umma_tf32(main_acc, a_hi0 + 2 * kk, b_hi0 + 2 * kk, idesc, (kb >= 2 || kk) ? 1u : 0u);
+                    umma_tf32(corr, a_lo0 + 2 * kk, b_hi0 + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                    umma_tf32(corr, a_hi0 + 2 * kk, b_lo0 + 2 * kk, idesc, 1u);
+                }
+                umma_commit(smem_u32(&bars[STAGES + s]));
             }
-            umma_commit(smem_u32(&bars[STAGES + s]));
+            __syncwarp();
         }
-        umma_commit(smem_u32(&bars[2 * STAGES]));
+        if (elect_one()) umma_commit(smem_u32(&bars[2 * STAGES]));
+        __syncwarp();
     }
     fence_before();
     __syncthreads();
