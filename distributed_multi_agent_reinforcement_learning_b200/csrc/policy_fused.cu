@@ -1244,8 +1244,9 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
             }
         }
     } else {
-        // ================================================================================= MMA issuer
-        if (lane == 0) {
+        // ================================================================================= MMA issuer (whole warp walks the
+        // unit program, one elected lane issues: see policy_pair_kernel)
+        {
             int it = 0, group = 0;
             bool fresh_group = true;
             for (int u = 0; u < na->n_units; ++u) {
@@ -1267,14 +1268,17 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
                         const uint32_t xa = smem_u32(X + kb * XKB), wb = smem_u32(Wst + s * M::STAGE);
                         // descriptors of the first K=16 slice; the next slices are +32 bytes = +2 in the (addr >> 4) field
                         const uint64_t a_hi0 = make_desc(xa), a_lo0 = make_desc(xa + TILE), b_hi0 = make_desc(wb), b_lo0 = make_desc(wb + lo_off);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint64_t a_hi = a_hi0 + 2 * kk, a_lo = a_lo0 + 2 * kk, b_hi = b_hi0 + 2 * kk, b_lo = b_lo0 + 2 * kk;
-                            umma_f16(acc, a_hi, b_hi, idesc, (un.accumulate || kb || kk) ? 1u : 0u);
-                            umma_f16(acc, a_lo, b_hi, idesc, 1u);
-                            umma_f16(acc, a_hi, b_lo, idesc, 1u);
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint64_t a_hi = a_hi0 + 2 * kk, a_lo = a_lo0 + 2 * kk, b_hi = b_hi0 + 2 * kk, b_lo = b_lo0 + 2 * kk;
+                                umma_f16(acc, a_hi, b_hi, idesc, (un.accumulate || kb || kk) ? 1u : 0u);
+                                umma_f16(acc, a_lo, b_hi, idesc, 1u);
+                                umma_f16(acc, a_hi, b_lo, idesc, 1u);
+                            }
+                            umma_commit(smem_u32(&bars[NST + s]));
                         }
-                        umma_commit(smem_u32(&bars[NST + s]));
+                        __syncwarp();
                     }
                 } else {
                     for (int st = 0; st < 2 * NKB; ++st, ++it) {          // stage = one plane of the weights: hi (pairs with A_hi and A_lo), then lo
@@ -1283,21 +1287,25 @@ policy_step_kernel(const __grid_constant__ StepArgs a)
                         tc_fence_after();
                         const uint32_t xa = smem_u32(X + kb * XKB);
                         const uint64_t a_hi0 = make_desc(xa), a_lo0 = make_desc(xa + TILE), b0 = make_desc(smem_u32(Wst + s * M::STAGE));
-                        if ((st & 1) == 0) {
+                        if (elect_one()) {
+                            if ((st & 1) == 0) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                umma_f16(acc, a_hi0 + 2 * kk, b0 + 2 * kk, idesc, (un.accumulate || kb || kk) ? 1u : 0u);
-                                umma_f16(acc, a_lo0 + 2 * kk, b0 + 2 * kk, idesc, 1u);
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    umma_f16(acc, a_hi0 + 2 * kk, b0 + 2 * kk, idesc, (un.accumulate || kb || kk) ? 1u : 0u);
+                                    umma_f16(acc, a_lo0 + 2 * kk, b0 + 2 * kk, idesc, 1u);
+                                }
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) umma_f16(acc, a_hi0 + 2 * kk, b0 + 2 * kk, idesc, 1u);
                             }
-                        } else {
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) umma_f16(acc, a_hi0 + 2 * kk, b0 + 2 * kk, idesc, 1u);
+                            umma_commit(smem_u32(&bars[NST + s]));
                         }
-                        umma_commit(smem_u32(&bars[NST + s]));
+                        __syncwarp();
                     }
                 }
                 if (un.last) {
-                    umma_commit(smem_u32(&bars[M::BAR_DONE]));
+                    if (elect_one()) umma_commit(smem_u32(&bars[M::BAR_DONE]));
+                    __syncwarp();
                     ++group;
                     fresh_group = true;
                 }
