@@ -1504,7 +1504,8 @@ __device__ void epi_cell_half_w(const Ctx &c, int l, int half, bool want_value, 
 
 // Launched with WW + 4 warps: the worker warps (whole warpgroups) take the registers that the loader / issuer warpgroup (two working
 // lanes, two idle warps) gives back with setmaxnreg, so the SIMT phases get 112 registers per thread instead of 96.
-constexpr int PAIR_WORKER_REGS = 112, PAIR_OTHER_REGS = 32;   // the CTA owns 640 x 96 registers: 512 x 104 + 128 x 56 fits; the issuer lane needs ~50
+constexpr int PAIR_WORKER_REGS = 112, PAIR_OTHER_REGS = 32;      // 16 worker warps: the CTA owns 640 x 96 registers
+constexpr int PAIR8_WORKER_REGS = 232, PAIR8_OTHER_REGS = 40;     //  8 worker warps (16-agent envs): 384 x 168   // the CTA owns 640 x 96 registers: 512 x 104 + 128 x 56 fits; the issuer lane needs ~50
 // PROF: per-phase cycle counters in registers (tools/fused_phase_profile.py, MARL_POLICY_PROFILE=1); the production instantiation
 // only writes the CTA's start / end %globaltimer, SM id and total cycles when a debug buffer is given, and keeps nothing live for it.
 #define PP_TICK(slot) do { if constexpr (PROF) { const long long now_ = clock64(); tk[slot] += now_ - t_prev; t_prev = now_; } } while (0)
@@ -1543,8 +1544,8 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp < WW) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PAIR_WORKER_REGS));
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PAIR_OTHER_REGS));
+    if (warp < WW) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WW == 16 ? PAIR_WORKER_REGS : PAIR8_WORKER_REGS));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WW == 16 ? PAIR_OTHER_REGS : PAIR8_OTHER_REGS));
 
     if (warp < WW) {
         // ================================================================================= workers
@@ -1581,7 +1582,8 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
             d[15] = (long long)smid;
         }
         const int D = a.depth, G0 = 7 + 3 * D, S_ACTOR = G0 + 9, S_CRITIC = G0 + 8;
-        const bool pair01 = (a.N == 8 || a.N == 4) && a.NW == 1;      // relations 0 and 1 computed once for both chains
+        constexpr int NA_BIG = Lay<WW>::RPW;                           // env size whose rows fill a warp: 8 (16 worker warps) or 16 (8)
+        const bool pair01 = (a.N == NA_BIG || (WW == 16 && a.N == 4)) && a.NW == 1;      // relations 0 and 1 computed once for both chains
         const uint32_t bar_ready0 = smem_u32(&bars[M::BAR_READY]), bar_done0 = smem_u32(&bars[M::BAR_DONE]);
 #pragma unroll 1
         for (int s = 0; s < S_ACTOR; ++s) {
@@ -1632,10 +1634,10 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
                         float w[4][8], b[4];
                         load_msg_weights(na, s >> 1, lane, w, b);
                         wait_prev();
-                        if (a.N == 8) {
-                            if (shared) phase_msg_pair01<8, WW>(c, smem, smem + M::XC_OFF, s >> 1, w, b);
-                            else phase_msg_fast<8, WW>(c, s >> 1, w, b);
-                        } else {
+                        if (a.N == NA_BIG) {
+                            if (shared) phase_msg_pair01<NA_BIG, WW>(c, smem, smem + M::XC_OFF, s >> 1, w, b);
+                            else phase_msg_fast<NA_BIG, WW>(c, s >> 1, w, b);
+                        } else if constexpr (WW == 16) {
                             if (shared) phase_msg_pair01<4, WW>(c, smem, smem + M::XC_OFF, s >> 1, w, b);
                             else phase_msg_fast<4, WW>(c, s >> 1, w, b);
                         }
@@ -1647,13 +1649,13 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
                 } else if (is_fcra_fill) {
                     // (one straight-line block per env size: through the size-dispatching wrappers the row array ended up on the
                     // stack - the loads were stored to local memory before the wait and read back after it)
-                    if (pair01 && a.O <= OXY_CAP && a.N == 8) {
+                    if (pair01 && a.O <= OXY_CAP && a.N == NA_BIG) {
                         float4 pre[Lay<WW>::RPW];
                         uint32_t words[4] = {0u, 0u, 0u, 0u};
-                        fcra_prefetch<8, WW>(c, fk, pre, words);
+                        fcra_prefetch<NA_BIG, WW>(c, fk, pre, words);
                         wait_prev();
-                        fcra_finish<8, WW>(c, pre, words);
-                    } else if (pair01 && a.O <= OXY_CAP && a.N == 4) {
+                        fcra_finish<NA_BIG, WW>(c, pre, words);
+                    } else if (WW == 16 && pair01 && a.O <= OXY_CAP && a.N == 4) {
                         float4 pre[Lay<WW>::RPW];
                         uint32_t words[4] = {0u, 0u, 0u, 0u};
                         fcra_prefetch<4, WW>(c, fk, pre, words);
@@ -1669,10 +1671,12 @@ policy_pair_kernel(const __grid_constant__ StepArgs a)
                     const bool want_value = l == 1 && na->head_w_eff != nullptr;
                     if (gsub == 0 || gsub == 2) {              // X <- h_prev (for W_hh of both halves) / X <- x again (for W_ih, half 1)
                         const float *src = gsub == 0 ? na->hidden_in + (int64_t)l * a.R * E : (l == 0 ? na->emb_out : na->hidden_out);
-                        float4 pre[8];
-                        rows_prefetch8<WW>(c, src, 0, pre);
+                        float4 pre[Lay<WW>::RPW / 8][8];
+#pragma unroll
+                        for (int q = 0; q < Lay<WW>::RPW / 8; ++q) rows_prefetch8<WW>(c, src, q, pre[q]);
                         wait_prev();
-                        rows_store8<WW>(c, 0, pre);
+#pragma unroll
+                        for (int q = 0; q < Lay<WW>::RPW / 8; ++q) rows_store8<WW>(c, q, pre[q]);
                         PP_TICK(3);
                     } else if (gsub == 1) {                    // W_hh(half 0) done: cell of half 0, h_prev read back from X
                         wait_prev();
@@ -2086,7 +2090,9 @@ extern "C" int marl_policy_rollout_step(const marl_policy_step *s, const marl_dh
         return MARL_OK;
     };
     // one CTA per SM: 16 worker warps unless the env-grouped message path needs a whole 16-agent env per warp
-    if (pair && getenv("MARL_POLICY_PROFILE")) rc = launch(pf::policy_pair_kernel<16, true>, (16 + 4) * 32, pf::MemPair::BYTES, false);
+    const bool pair8 = pair && s->N == 16 && s->O <= pf::OXY_CAP;       // 16-agent envs: a whole env per warp needs 8 worker warps
+    if (pair8) rc = launch(pf::policy_pair_kernel<8, false>, (8 + 4) * 32, pf::MemPair::BYTES, false);
+    else if (pair && getenv("MARL_POLICY_PROFILE")) rc = launch(pf::policy_pair_kernel<16, true>, (16 + 4) * 32, pf::MemPair::BYTES, false);
     else if (pair) rc = launch(pf::policy_pair_kernel<16, false>, (16 + 4) * 32, pf::MemPair::BYTES, false);
     else if (dual) rc = launch(pf::policy_step_kernel<8, true>, pf::Lay<8>::THREADS, pf::Mem<true>::BYTES, true);
     else if (!(s->N == 16 && s->O <= pf::OXY_CAP)) rc = launch(pf::policy_step_kernel<16, false>, pf::Lay<16>::THREADS, pf::Mem<false>::BYTES, false);

@@ -103,8 +103,8 @@ class FusedRolloutStep:
         SM, 3 = both networks' chains of a tile interleaved in one CTA.  Variant 2 reads the previous hidden state from one
         buffer and writes the new one to another; afterwards the two tensors trade their storage, so for the caller `ha` / `hc`
         are still updated "in place" (views taken before the call keep the old state)."""
-        if int(variant) == 0 and DEFAULT_VARIANT == 3 and "actor" in nets and "critic" in nets and not (engine.N == 16 and engine.O <= 256):
-            variant = 3          # (16-agent envs keep the 8-worker-warp kernel: their message path needs a whole env per warp)
+        if int(variant) == 0 and DEFAULT_VARIANT == 3 and "actor" in nets and "critic" in nets:
+            variant = 3          # (16-agent envs run the pair kernel with 8 worker warps: their message path needs a whole env per warp)
         if int(variant) == 3 and not ("actor" in nets and "critic" in nets):
             variant = 1          # a single network (the critic-only bootstrap step): nothing to interleave
         s = PolicyStep()
