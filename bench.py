@@ -554,6 +554,8 @@ def run_ours(args):
             torch.cuda.synchronize()
         wall = ev0.elapsed_time(ev1)
         rec = dbg.cpu().numpy()
+        if os.environ.get("MARL_BENCH_TIMELINE"):          # tools: per-CTA (cycles, start ns, end ns, SM id) of every policy launch
+            np.savez_compressed(os.environ["MARL_BENCH_TIMELINE"], rec=rec[..., 12:16], wall_ms=wall)
         used = rec[..., 14] > 0
         starts = np.where(used, rec[..., 13], np.iinfo(np.int64).max).min(axis=2)      # [T, G] ns
         ends = np.where(used, rec[..., 14], 0).max(axis=2)

@@ -4,16 +4,22 @@
 // Replanning: one warp (= one CTA) per environment, whole search state in shared memory: the blocked-node bitmap
 // as one 64-bit column per x, g (fp64 — exact tie-breaking needs the reference's summation order), parent (u16)
 // and the OPEN set.  heapq's pop order is the total order of (f, (x, y)) tuples (ties only between identical
-// items), so ANY correct priority queue pops the same sequence; here OPEN is an unsorted shared-memory array and a
-// pop is a warp-wide arg-min (strided scan + three REDUX steps on the order-preserving integer image of f, then the
-// node id), which costs a few hundred cycles instead of a lane-serial sift.  The 8 neighbours are relaxed by 8
-// lanes in parallel and appended with a ballot prefix.  Obstacle inflation / pursuer inflation / the half-open view
-// window of Evader.rescan are separable bit operations on the columns.
+// items), so ANY correct priority queue pops the same sequence.  The search is one warp walking a dependent chain (about six
+// cycles per instruction), so a pop is built to be SHORT and independent of |OPEN|: OPEN is an unsorted shared-memory array cut
+// into 32 stripes (slot i belongs to stripe i % 32, stored stripe-major); lane l keeps the minimum of stripe l in registers, so
+// a pop is three REDUX steps over those 32 cached minima (order-preserving integer image of f, then node id and slot packed in
+// one word) - no scan.  The popped slot is refilled by the first neighbour pushed in the same pop (by the last slot's entry
+// when nothing is pushed), further pushes are appended round-robin over the stripes; afterwards only the popped stripe's minimum has to be recomputed, by all
+// 32 lanes together (its <= 49 entries are contiguous), and the lanes that own an appended slot fold it into their minimum.
+// The 8 neighbours are relaxed by 8 lanes in parallel; blocked nodes carry g = -1 from the start, so `new_cost < g` rejects
+// them without a bitmap test.  Obstacle inflation / pursuer inflation / the half-open view window of Evader.rescan are
+// separable bit operations on the columns.
 #include "evader_move.cuh"
 
 namespace marl {
 
-static constexpr int kOpenCap = 1536;
+static constexpr int kStripeCap = 49;               // OPEN entries per stripe; odd, so consecutive slots (different stripes) fall into different banks
+static constexpr int kOpenCap = 32 * kStripeCap;    // 1568 entries
 static constexpr int kPopBudget = 192;   // pops before the reachability check (p99 of successful searches is ~200)
 
 struct EvaderArgs {
@@ -49,7 +55,7 @@ __device__ __forceinline__ uint64_t dilate_y(uint64_t c, int e, uint64_t hmask)
 
 struct SearchSmem {
     double *g;        // [NODES]
-    double *of;       // [kOpenCap] f of OPEN entries
+    double *of;       // [kOpenCap] f of OPEN entries, stripe-major: slot i at (i % 32) * kStripeCap + i / 32
     uint64_t *mov;    // [W1]
     uint64_t *blk;    // [W1]
     uint16_t *par;    // [NODES]
@@ -125,7 +131,8 @@ __device__ int replan_warp(const EnvDev &c, const SearchSmem &sm, const uint32_t
     __syncwarp();
     const int ux = (lane == 0 || lane == 1 || lane == 7) ? -1 : ((lane >= 3 && lane <= 5) ? 1 : 0);   // astar.py:11-12
     const int uy = (lane >= 1 && lane <= 3) ? 1 : ((lane >= 5 && lane <= 7) ? -1 : 0);
-    const double diag = sqrt(2.0);   // math.hypot(1, 1)
+    const double step_cost = (ux != 0 && uy != 0) ? sqrt(2.0) : 1.0;   // math.hypot(1, 1)
+    const int dn = ux * kNodeStride + uy;
     const int start = (cx << kNodeShift) | cy, goal = (tx << kNodeShift) | ty;
     int n_path = 1;
     for (int e = c.e_extend_dis; e >= 0; --e) {
@@ -151,84 +158,126 @@ __device__ int replan_warp(const EnvDev &c, const SearchSmem &sm, const uint32_t
             }
             sm.blk[x] = st | (view & pr);
         }
-        for (int n = lane; n < NODES; n += 32) sm.g[n] = INFINITY;
+        __syncwarp();
+        // g: +inf on free nodes, -1 on blocked ones (column-wise: lane l writes rows l and l + 32 of every column)
+        for (int x = 0; x < W1; ++x) {
+            const uint64_t col = sm.blk[x];
+            const unsigned lo = (unsigned)col, hi = (unsigned)(col >> 32);
+            sm.g[(x << kNodeShift) + lane] = ((lo >> lane) & 1u) ? -1.0 : (double)INFINITY;
+            sm.g[(x << kNodeShift) + 32 + lane] = ((hi >> lane) & 1u) ? -1.0 : (double)INFINITY;
+        }
         __syncwarp();
         // ---- AStar_2D.searching (astar.py:26-73) ----
         n_path = 1;
         const bool goal_blocked = (sm.blk[tx] >> ty) & 1ull;
-        if (!goal_blocked) {
+        // a blocked start expands nothing (astar.py:56-60 tests both ends of every move): OPEN runs empty after the first pop
+        const bool start_blocked = (sm.blk[cx] >> cy) & 1ull;
+        if (!goal_blocked && !start_blocked) {
+            unsigned long long *const ofb = reinterpret_cast<unsigned long long *>(sm.of);
+            unsigned c_hi = 0xffffffffu, c_lo = 0xffffffffu, c_tag = 0xffffffffu;   // minimum of this lane's stripe: f bits, node << 11 | slot
             if (lane == 0) {
+                const double f0 = 0.0 + 2.5 * (double)(abs(tx - cx) + abs(ty - cy));
                 sm.g[start] = 0.0;
                 sm.par[start] = (uint16_t)start;
-                sm.of[0] = 0.0 + 2.5 * (double)(abs(tx - cx) + abs(ty - cy));
+                sm.of[0] = f0;
                 sm.on[0] = (uint16_t)start;
+                const unsigned long long k0 = (unsigned long long)__double_as_longlong(f0);     // f >= 0: order-preserving
+                c_hi = (unsigned)(k0 >> 32); c_lo = (unsigned)k0; c_tag = (unsigned)start << 11;
             }
-            int n_open = 1, pops = 0;
+            int extent = 1, pops = 0;   // slots [0, extent) are in use
             __syncwarp();
             bool reached = false;
-            while (n_open > 0) {
+            for (;;) {
                 if (++pops == kPopBudget) {   // long search: make sure it can succeed before spending more on it
                     if (!goal_reachable(sm, sm.blk + W1, W1, H1, cx, cy, tx, ty)) break;
                 }
-                // ---- pop: warp-wide arg-min of (f, node) over the unsorted OPEN array ----
-                unsigned long long best = ~0ull;
-                int best_node = 0x7fffffff, best_idx = -1;
-                for (int i = lane; i < n_open; i += 32) {
-                    const unsigned long long k = (unsigned long long)__double_as_longlong(sm.of[i]);   // f >= 0: order-preserving
-                    const int nd = sm.on[i];
-                    if (k < best || (k == best && nd < best_node)) { best = k; best_node = nd; best_idx = i; }
-                }
-                const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
-                const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-                unsigned owner_mask = __ballot_sync(0xffffffffu, hi == mhi && best_idx >= 0);
-                if (__popc(owner_mask) > 1) {            // several lanes share the high word of the smallest f: low word, then the node id
-                    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
-                    const bool cand = (hi == mhi) && (lo == mlo) && best_idx >= 0;
-                    const unsigned mnode = __reduce_min_sync(0xffffffffu, cand ? (unsigned)best_node : 0xffffffffu);
-                    owner_mask = __ballot_sync(0xffffffffu, cand && (unsigned)best_node == mnode);
-                }
-                const int owner = __ffs(owner_mask) - 1;
-                const int s = __shfl_sync(0xffffffffu, best_node, owner);
-                --n_open;
-                if (lane == owner && best_idx != n_open) {   // remove: move the last entry into the hole
-                    sm.of[best_idx] = sm.of[n_open];
-                    sm.on[best_idx] = sm.on[n_open];
-                }
-                __syncwarp();
+                // ---- pop: arg-min of (f, node) over the 32 cached stripe minima ----
+                const unsigned mhi = __reduce_min_sync(0xffffffffu, c_hi);
+                if (mhi == 0xffffffffu) break;                       // OPEN is empty
+                const bool c1 = c_hi == mhi;
+                const unsigned mlo = __reduce_min_sync(0xffffffffu, c1 ? c_lo : 0xffffffffu);
+                const unsigned tag = __reduce_min_sync(0xffffffffu, (c1 && c_lo == mlo) ? c_tag : 0xffffffffu);
+                const int s = (int)(tag >> 11), slot = (int)(tag & 2047u);
                 if (s == goal) { reached = true; break; }
                 // ---- relax the 8 neighbours (astar.py:56-65) on lanes 0..7 ----
                 const int sx = s >> kNodeShift, sy = s & (kNodeStride - 1);
-                bool push = false;
+                const int nx = sx + ux, ny = sy + uy;
+                const bool inside = lane < 8 && (unsigned)nx <= (unsigned)W && (unsigned)ny <= (unsigned)H;
+                const int nn = inside ? s + dn : s;                  // (outside: re-reads g[s], which new_cost never beats)
+                const double g_s = sm.g[s], g_n = sm.g[nn];
+                const double nc = dadd(g_s, step_cost);
+                const bool push = inside && nc < g_n;
                 double nf = 0.0;
-                int nn = 0;
-                if (lane < 8) {
-                    const int nx = sx + ux, ny = sy + uy;
-                    const bool inside = nx >= 0 && nx <= W && ny >= 0 && ny <= H;
-                    // all four shared-memory reads are issued together (clamped indices) instead of one per nested test: the relaxation
-                    // is on the critical path of every pop
-                    const int nxc = inside ? nx : sx, nyc = inside ? ny : sy;
-                    nn = (nxc << kNodeShift) | nyc;
-                    const uint64_t col_s = sm.blk[sx], col_n = sm.blk[nxc];
-                    const double g_s = sm.g[s], g_n = sm.g[nn];
-                    const bool bad = !inside || ((col_s >> sy) & 1ull) || ((col_n >> nyc) & 1ull);
-                    const double nc = dadd(g_s, (ux != 0 && uy != 0) ? diag : 1.0);
-                    if (!bad && nc < g_n) {
-                        sm.g[nn] = nc;
-                        sm.par[nn] = (uint16_t)s;
-                        nf = dadd(nc, dmul(2.5, (double)(abs(tx - nx) + abs(ty - ny))));
-                        push = true;
-                    }
+                if (push) {
+                    sm.g[nn] = nc;
+                    sm.par[nn] = (uint16_t)s;
+                    nf = __fma_rn(2.5, (double)(abs(tx - nx) + abs(ty - ny)), nc);   // 2.5 h is exact: same bits as nc + 2.5 * h
                 }
                 const unsigned pm = __ballot_sync(0xffffffffu, push);
                 const int n_push = __popc(pm);
-                if (n_open + n_push > kOpenCap) { status |= EV_HEAP_OVERFLOW; n_open = 0; break; }
-                if (push) {
-                    const int slot = n_open + __popc(pm & ((1u << lane) - 1u));
-                    sm.of[slot] = nf;
-                    sm.on[slot] = (uint16_t)nn;
+                const int n_app = max(n_push - 1, 0);
+                if (extent + n_app > kOpenCap) { status |= EV_HEAP_OVERFLOW; break; }
+                const int o = slot & 31;
+                int o2 = -1;                                         // second stripe to refresh (dead-end pops only)
+                if (push) {   // the first pusher refills the popped slot, the others append
+                    const int rank = __popc(pm & ((1u << lane) - 1u));
+                    const int i = rank == 0 ? slot : extent + rank - 1;
+                    const int p = (i & 31) * kStripeCap + (i >> 5);
+                    sm.of[p] = nf;
+                    sm.on[p] = (uint16_t)nn;
                 }
-                n_open += n_push;
+                if (n_push == 0) {                                   // dead end: the last slot's entry moves into the hole
+                    const int last = extent - 1;
+                    if (slot != last && lane == 0) {
+                        const int ps = o * kStripeCap + (slot >> 5), pl = (last & 31) * kStripeCap + (last >> 5);
+                        ofb[ps] = ofb[pl];
+                        sm.on[ps] = sm.on[pl];
+                    }
+                    extent = last;
+                    o2 = last & 31;
+                }
                 __syncwarp();
+                {   // lanes that own an appended slot fold it into their stripe minimum
+                    const int d = (lane - extent) & 31;
+                    if (d < n_app) {
+                        const int i = extent + d, p = lane * kStripeCap + (i >> 5);
+                        const unsigned long long k = ofb[p];
+                        const unsigned t = ((unsigned)sm.on[p] << 11) | (unsigned)i;
+                        const unsigned khi = (unsigned)(k >> 32), klo = (unsigned)k;
+                        if (khi < c_hi || (khi == c_hi && (klo < c_lo || (klo == c_lo && t < c_tag)))) { c_hi = khi; c_lo = klo; c_tag = t; }
+                    }
+                }
+                extent += n_app;
+                // ---- the popped stripe's new minimum (all lanes read its contiguous entries; the owner keeps the result) ----
+                for (int st = o;;) {
+                    const int len = (extent - st + 31) >> 5;         // slots st, st + 32, ... below extent
+                    if (len <= 1) {
+                        if (lane == st) {
+                            c_hi = c_lo = c_tag = 0xffffffffu;
+                            if (len == 1) {
+                                const int p = st * kStripeCap;
+                                const unsigned long long k = ofb[p];
+                                c_hi = (unsigned)(k >> 32); c_lo = (unsigned)k; c_tag = ((unsigned)sm.on[p] << 11) | (unsigned)st;
+                            }
+                        }
+                    } else {
+                        unsigned b_hi = 0xffffffffu, b_lo = 0xffffffffu, b_tag = 0xffffffffu;
+                        for (int j = lane; j < len; j += 32) {
+                            const int p = st * kStripeCap + j;
+                            const unsigned long long k = ofb[p];
+                            const unsigned t = ((unsigned)sm.on[p] << 11) | (unsigned)((j << 5) | st);
+                            const unsigned khi = (unsigned)(k >> 32), klo = (unsigned)k;
+                            if (khi < b_hi || (khi == b_hi && (klo < b_lo || (klo == b_lo && t < b_tag)))) { b_hi = khi; b_lo = klo; b_tag = t; }
+                        }
+                        const unsigned rhi = __reduce_min_sync(0xffffffffu, b_hi);
+                        const bool r1 = b_hi == rhi;
+                        const unsigned rlo = __reduce_min_sync(0xffffffffu, r1 ? b_lo : 0xffffffffu);
+                        const unsigned rtag = __reduce_min_sync(0xffffffffu, (r1 && b_lo == rlo) ? b_tag : 0xffffffffu);
+                        if (lane == st) { c_hi = rhi; c_lo = rlo; c_tag = rtag; }
+                    }
+                    if (o2 < 0 || o2 == st) break;
+                    st = o2;                                         // the stripe that lost its last slot
+                }
             }
             if (reached) {   // extract_path (astar.py:130-146): [goal, ..., start]
                 if (lane == 0) {
