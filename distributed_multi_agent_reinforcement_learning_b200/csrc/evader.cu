@@ -20,7 +20,7 @@ namespace marl {
 
 static constexpr int kStripeCap = 49;               // OPEN entries per stripe; odd, so consecutive slots (different stripes) fall into different banks
 static constexpr int kOpenCap = 32 * kStripeCap;    // 1568 entries
-static constexpr int kPopBudget = 192;   // pops before the reachability check (p99 of successful searches is ~200)
+static constexpr int kPopBudget = 192;   // pops before the reachability check (p99 of successful searches is ~200; 32 .. 192 time the same)
 
 struct EvaderArgs {
     int B, path_cap, tape_len;
@@ -199,26 +199,75 @@ __device__ int replan_warp(const EnvDev &c, const SearchSmem &sm, const uint32_t
                 const unsigned tag = __reduce_min_sync(0xffffffffu, (c1 && c_lo == mlo) ? c_tag : 0xffffffffu);
                 const int s = (int)(tag >> 11), slot = (int)(tag & 2047u);
                 if (s == goal) { reached = true; break; }
-                // ---- relax the 8 neighbours (astar.py:56-65) on lanes 0..7 ----
+                const int o = slot & 31, jpop = slot >> 5;           // the popped entry: stripe o, position jpop
+                // ---- (R) the minimum of stripe o WITHOUT the popped entry: all lanes read its (contiguous) entries.  Independent of
+                // the relaxation (B) below - the two dependent chains are written interleaved so that they overlap ----
+                const int len_o = (extent - o + 31) >> 5;            // slots o, o + 32, ... below extent (<= kStripeCap <= 64)
+                unsigned b_hi = 0xffffffffu, b_lo = 0xffffffffu, b_tag = 0xffffffffu;
+                {
+                    const int j0 = lane, j1 = lane + 32;
+                    const bool v0 = j0 < len_o && j0 != jpop, v1 = j1 < len_o && j1 != jpop;
+                    unsigned long long k0 = ~0ull, k1 = ~0ull;
+                    unsigned t0 = 0xffffffffu, t1 = 0xffffffffu;
+                    if (v0) { const int p = o * kStripeCap + j0; k0 = ofb[p]; t0 = ((unsigned)sm.on[p] << 11) | (unsigned)((j0 << 5) | o); }
+                    if (v1) { const int p = o * kStripeCap + j1; k1 = ofb[p]; t1 = ((unsigned)sm.on[p] << 11) | (unsigned)((j1 << 5) | o); }
+                    const bool second = k1 < k0 || (k1 == k0 && t1 < t0);
+                    const unsigned long long kb = second ? k1 : k0;
+                    b_hi = (unsigned)(kb >> 32); b_lo = (unsigned)kb; b_tag = second ? t1 : t0;
+                }
+                // ---- (B) relax the 8 neighbours (astar.py:56-65) on lanes 0..7 ----
                 const int sx = s >> kNodeShift, sy = s & (kNodeStride - 1);
                 const int nx = sx + ux, ny = sy + uy;
                 const bool inside = lane < 8 && (unsigned)nx <= (unsigned)W && (unsigned)ny <= (unsigned)H;
                 const int nn = inside ? s + dn : s;                  // (outside: re-reads g[s], which new_cost never beats)
                 const double g_s = sm.g[s], g_n = sm.g[nn];
-                const double nc = dadd(g_s, step_cost);
-                const bool push = inside && nc < g_n;
-                double nf = 0.0;
+                const unsigned rhi = __reduce_min_sync(0xffffffffu, b_hi);                                   // (R)
+                const double nc = dadd(g_s, step_cost);                                                      // (B)
+                const bool r1 = b_hi == rhi;
+                const unsigned rlo = __reduce_min_sync(0xffffffffu, r1 ? b_lo : 0xffffffffu);                // (R)
+                const bool push = inside && nc < g_n;                                                        // (B)
+                const double nf = __fma_rn(2.5, (double)(abs(tx - nx) + abs(ty - ny)), nc);                  // 2.5 h is exact: same bits as nc + 2.5 * h
+                const unsigned rtag = __reduce_min_sync(0xffffffffu, (r1 && b_lo == rlo) ? b_tag : 0xffffffffu);   // (R)
                 if (push) {
                     sm.g[nn] = nc;
                     sm.par[nn] = (uint16_t)s;
-                    nf = __fma_rn(2.5, (double)(abs(tx - nx) + abs(ty - ny)), nc);   // 2.5 h is exact: same bits as nc + 2.5 * h
                 }
                 const unsigned pm = __ballot_sync(0xffffffffu, push);
                 const int n_push = __popc(pm);
                 const int n_app = max(n_push - 1, 0);
                 if (extent + n_app > kOpenCap) { status |= EV_HEAP_OVERFLOW; break; }
-                const int o = slot & 31;
-                int o2 = -1;                                         // second stripe to refresh (dead-end pops only)
+                if (n_push == 0) {
+                    // ---- dead end (one pop in ten): the last slot's entry moves into the hole; the two stripes involved are re-read ----
+                    const int last = extent - 1;
+                    if (slot != last && lane == 0) {
+                        const int ps = o * kStripeCap + jpop, pl = (last & 31) * kStripeCap + (last >> 5);
+                        ofb[ps] = ofb[pl];
+                        sm.on[ps] = sm.on[pl];
+                    }
+                    extent = last;
+                    const int o2 = last & 31;
+                    __syncwarp();
+                    for (int st = o;;) {
+                        const int len = (extent - st + 31) >> 5;
+                        unsigned q_hi = 0xffffffffu, q_lo = 0xffffffffu, q_tag = 0xffffffffu;
+                        for (int j = lane; j < len; j += 32) {
+                            const int p = st * kStripeCap + j;
+                            const unsigned long long k = ofb[p];
+                            const unsigned t = ((unsigned)sm.on[p] << 11) | (unsigned)((j << 5) | st);
+                            const unsigned khi = (unsigned)(k >> 32), klo = (unsigned)k;
+                            if (khi < q_hi || (khi == q_hi && (klo < q_lo || (klo == q_lo && t < q_tag)))) { q_hi = khi; q_lo = klo; q_tag = t; }
+                        }
+                        const unsigned uhi = __reduce_min_sync(0xffffffffu, q_hi);
+                        const bool u1 = q_hi == uhi;
+                        const unsigned ulo = __reduce_min_sync(0xffffffffu, u1 ? q_lo : 0xffffffffu);
+                        const unsigned utag = __reduce_min_sync(0xffffffffu, (u1 && q_lo == ulo) ? q_tag : 0xffffffffu);
+                        if (lane == st) { c_hi = uhi; c_lo = ulo; c_tag = utag; }
+                        if (o2 == st) break;
+                        st = o2;                                     // the stripe that lost its last slot
+                    }
+                    continue;
+                }
+                if (lane == o) { c_hi = rhi; c_lo = rlo; c_tag = rtag; }
                 if (push) {   // the first pusher refills the popped slot, the others append
                     const int rank = __popc(pm & ((1u << lane) - 1u));
                     const int i = rank == 0 ? slot : extent + rank - 1;
@@ -226,58 +275,27 @@ __device__ int replan_warp(const EnvDev &c, const SearchSmem &sm, const uint32_t
                     sm.of[p] = nf;
                     sm.on[p] = (uint16_t)nn;
                 }
-                if (n_push == 0) {                                   // dead end: the last slot's entry moves into the hole
-                    const int last = extent - 1;
-                    if (slot != last && lane == 0) {
-                        const int ps = o * kStripeCap + (slot >> 5), pl = (last & 31) * kStripeCap + (last >> 5);
-                        ofb[ps] = ofb[pl];
-                        sm.on[ps] = sm.on[pl];
-                    }
-                    extent = last;
-                    o2 = last & 31;
-                }
                 __syncwarp();
-                {   // lanes that own an appended slot fold it into their stripe minimum
+                {   // the new entries are folded into their stripes' minima: lane o takes the refilled slot, the owner of an appended slot that one
                     const int d = (lane - extent) & 31;
-                    if (d < n_app) {
-                        const int i = extent + d, p = lane * kStripeCap + (i >> 5);
+                    const bool app = d < n_app;
+                    const int ia = extent + d;
+                    if (app) {
+                        const int p = lane * kStripeCap + (ia >> 5);
                         const unsigned long long k = ofb[p];
-                        const unsigned t = ((unsigned)sm.on[p] << 11) | (unsigned)i;
+                        const unsigned t = ((unsigned)sm.on[p] << 11) | (unsigned)ia;
+                        const unsigned khi = (unsigned)(k >> 32), klo = (unsigned)k;
+                        if (khi < c_hi || (khi == c_hi && (klo < c_lo || (klo == c_lo && t < c_tag)))) { c_hi = khi; c_lo = klo; c_tag = t; }
+                    }
+                    if (lane == o) {
+                        const int p = o * kStripeCap + jpop;
+                        const unsigned long long k = ofb[p];
+                        const unsigned t = ((unsigned)sm.on[p] << 11) | (unsigned)slot;
                         const unsigned khi = (unsigned)(k >> 32), klo = (unsigned)k;
                         if (khi < c_hi || (khi == c_hi && (klo < c_lo || (klo == c_lo && t < c_tag)))) { c_hi = khi; c_lo = klo; c_tag = t; }
                     }
                 }
                 extent += n_app;
-                // ---- the popped stripe's new minimum (all lanes read its contiguous entries; the owner keeps the result) ----
-                for (int st = o;;) {
-                    const int len = (extent - st + 31) >> 5;         // slots st, st + 32, ... below extent
-                    if (len <= 1) {
-                        if (lane == st) {
-                            c_hi = c_lo = c_tag = 0xffffffffu;
-                            if (len == 1) {
-                                const int p = st * kStripeCap;
-                                const unsigned long long k = ofb[p];
-                                c_hi = (unsigned)(k >> 32); c_lo = (unsigned)k; c_tag = ((unsigned)sm.on[p] << 11) | (unsigned)st;
-                            }
-                        }
-                    } else {
-                        unsigned b_hi = 0xffffffffu, b_lo = 0xffffffffu, b_tag = 0xffffffffu;
-                        for (int j = lane; j < len; j += 32) {
-                            const int p = st * kStripeCap + j;
-                            const unsigned long long k = ofb[p];
-                            const unsigned t = ((unsigned)sm.on[p] << 11) | (unsigned)((j << 5) | st);
-                            const unsigned khi = (unsigned)(k >> 32), klo = (unsigned)k;
-                            if (khi < b_hi || (khi == b_hi && (klo < b_lo || (klo == b_lo && t < b_tag)))) { b_hi = khi; b_lo = klo; b_tag = t; }
-                        }
-                        const unsigned rhi = __reduce_min_sync(0xffffffffu, b_hi);
-                        const bool r1 = b_hi == rhi;
-                        const unsigned rlo = __reduce_min_sync(0xffffffffu, r1 ? b_lo : 0xffffffffu);
-                        const unsigned rtag = __reduce_min_sync(0xffffffffu, (r1 && b_lo == rlo) ? b_tag : 0xffffffffu);
-                        if (lane == st) { c_hi = rhi; c_lo = rlo; c_tag = rtag; }
-                    }
-                    if (o2 < 0 || o2 == st) break;
-                    st = o2;                                         // the stripe that lost its last slot
-                }
             }
             if (reached) {   // extract_path (astar.py:130-146): [goal, ..., start]
                 if (lane == 0) {
