@@ -6,8 +6,9 @@ namespace marl {
 
 // ---- 3a: Welford (DHGN/normalization.py:4-35), one running estimate per env -----------------------------
 // Block = whole envs only, so the shared per-env counter n can be read by every agent thread before it is bumped.
+template <typename X>
 __global__ void __launch_bounds__(128)
-welford_kernel(int B, int N, int epb, const int32_t *__restrict__ reward, long long *__restrict__ n_arr,
+welford_kernel(int B, int N, int epb, const X *__restrict__ reward, long long *__restrict__ n_arr,
                double *__restrict__ mean, double *__restrict__ S, double *__restrict__ sd, float *__restrict__ out,
                int update)
 {
@@ -139,9 +140,21 @@ extern "C" int marl_welford_update(int32_t B, int32_t N, const int32_t *d_reward
     MARL_REQUIRE(d_reward && d_n && d_mean && d_S && d_std && d_out, "marl_welford_update: null pointer");
     const int epb = 128 / N;
     const int blocks = (B + epb - 1) / epb;
-    welford_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(B, N, epb, d_reward, (long long *)d_n, d_mean, d_S, d_std,
-                                                             d_out, update);
+    welford_kernel<int32_t><<<blocks, 128, 0, (cudaStream_t)stream>>>(B, N, epb, d_reward, (long long *)d_n, d_mean, d_S, d_std,
+                                                                      d_out, update);
     return check_launch("welford_kernel");
+}
+
+extern "C" int marl_welford_update_f64(int32_t B, int32_t N, const double *d_x, int64_t *d_n, double *d_mean,
+                                       double *d_S, double *d_std, float *d_out, int32_t update, void *stream)
+{
+    MARL_REQUIRE(B > 0 && N > 0 && N <= 128, "marl_welford_update_f64: B=%d N=%d", B, N);
+    MARL_REQUIRE(d_x && d_n && d_mean && d_S && d_std && d_out, "marl_welford_update_f64: null pointer");
+    const int epb = 128 / N;
+    const int blocks = (B + epb - 1) / epb;
+    welford_kernel<double><<<blocks, 128, 0, (cudaStream_t)stream>>>(B, N, epb, d_x, (long long *)d_n, d_mean, d_S, d_std,
+                                                                     d_out, update);
+    return check_launch("welford_kernel<double>");
 }
 
 extern "C" int64_t marl_gae_workspace_bytes(int32_t B, int32_t T, int32_t N)

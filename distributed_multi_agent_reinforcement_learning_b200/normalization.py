@@ -28,6 +28,14 @@ class RunningMeanStd:
     def update(self, x):
         self._run(x, True)
 
+    def update_f64(self, x):
+        """RunningMeanStd.update for samples that are not integers (the discounted return of RewardScaling)."""
+        x = torch.as_tensor(np.asarray(x, dtype=np.float64).reshape(1, self.shape), device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().marl_welford_update_f64(1, self.shape, _lib.ptr(x), _lib.ptr(self._n), _lib.ptr(self._mean),
+                                                          _lib.ptr(self._S), _lib.ptr(self._std), _lib.ptr(self._out), 1,
+                                                          _lib.stream_ptr()), "marl_welford_update_f64")
+
     def _run(self, x, update):
         a = np.asarray(x, dtype=np.float64)
         if not np.array_equal(a, np.rint(a)):             # checked BEFORE the cast: a non-integer reward must not be truncated silently
@@ -71,7 +79,8 @@ class Normalization:
 
 
 class RewardScaling:
-    """DHGN/normalization.py:38-52 (unused by the reference's training loop; kept for API completeness)."""
+    """DHGN/normalization.py:38-52: x / (std of the running discounted return + 1e-8).  The reference's training loop never
+    builds one (it normalises with `Normalization`); same class, same arithmetic, the estimate updated by the f64 Welford entry."""
 
     def __init__(self, shape, gamma, device=None):
         self.shape, self.gamma = shape, gamma
@@ -79,8 +88,10 @@ class RewardScaling:
         self.R = np.zeros(self.shape)
 
     def __call__(self, x):
-        raise NotImplementedError("RewardScaling feeds non-integer returns to the running estimate; the Welford kernel "
-                                  "of this engine is specialised to the env's integer rewards")
+        x = np.asarray(x, dtype=np.float64)
+        self.R = self.gamma * self.R + x
+        self.running_ms.update_f64(self.R)
+        return x / (self.running_ms.std + 1e-8)
 
     def reset(self):
         self.R = np.zeros(self.shape)

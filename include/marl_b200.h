@@ -152,6 +152,10 @@ int marl_env_reset_place(const marl_env_params *p, int32_t B, int32_t M, const u
  * d_out f32 [B,N] = float32((x-mean)/(std+1e-8)) (DHGN/mappo_parallel.py:795-797). update != 0 => update stats. */
 int marl_welford_update(int32_t B, int32_t N, const int32_t *d_reward, int64_t *d_n, double *d_mean,
                         double *d_S, double *d_std, float *d_out, int32_t update, void *stream);
+/* Same estimate fed with f64 samples d_x [B,N]: RunningMeanStd.update on the discounted return of RewardScaling
+ * (DHGN/normalization.py:38-52), whose samples are not integers. */
+int marl_welford_update_f64(int32_t B, int32_t N, const double *d_x, int64_t *d_n, double *d_mean,
+                            double *d_S, double *d_std, float *d_out, int32_t update, void *stream);
 
 /* ---- kernel 3b: GAE + advantage normalisation ----------------------------------------------------
  * Replaces MAPPO.train's GAE block (DHGN/mappo_parallel.py:643-658).  time_major == 0: r, active f32 [B,T,N],

@@ -111,3 +111,23 @@ def test_gather_rows(row_elems, dtype):
     _lib.check(L.marl_gather_rows(_lib.ptr(src), _lib.ptr(dst2), _lib.ptr(seq), 20, row_elems * src.element_size(), Bsrc,
                                   _lib.stream_ptr()))
     assert torch.equal(dst2, src[10:30])
+
+
+def test_reward_scaling_matches_reference():
+    """RewardScaling (DHGN/normalization.py:38-52) on the f64 Welford entry against the reference's own outputs
+    (tests/golden/reward_scaling.npz, oracle/gen_golden_reward_scaling.py): two episodes with a reset() between them."""
+    from conftest import golden
+    from distributed_multi_agent_reinforcement_learning_b200.normalization import RewardScaling
+    fx = golden("reward_scaling")
+    x, T = fx["x"], fx["x"].shape[0] // 2
+    rs = RewardScaling(shape=x.shape[1], gamma=float(fx["gamma"]))
+    for t in range(2 * T):
+        if t == T:
+            rs.reset()
+        np.testing.assert_allclose(rs(x[t]), fx["out"][t], rtol=1e-12, atol=0)
+    ms = rs.running_ms
+    assert ms.n == int(fx["n"])
+    np.testing.assert_allclose(ms.mean, fx["mean"], rtol=1e-12)
+    np.testing.assert_allclose(ms.S, fx["S"], rtol=1e-12)
+    np.testing.assert_allclose(ms.std, fx["std"], rtol=1e-12)
+    np.testing.assert_allclose(rs.R, fx["R"], rtol=1e-14)
