@@ -402,13 +402,17 @@ ppo_head_kernel(HeadArgs h)
         else if (s1 < s2) dmin = adv;
         else if (s1 == s2) dmin = 0.5f * adv;
         const float dlogp = -dmin * ratio * on;           // d(actor term * active)/d logp(a)
-        const float vo = h.v_old[r], vt = h.v_target[r];
-        const float dv = v - vo;
-        const float ec = fminf(fmaxf(dv, -h.eps), h.eps) + vo - vt, eo = v - vt;
-        const float c1 = ec * ec, c2 = eo * eo;
-        const float c_term = fmaxf(c1, c2);
-        const float gc = (dv >= -h.eps && dv <= h.eps) ? 2.f * ec : 0.f, go = 2.f * eo;
-        const float dval = (c1 > c2 ? gc : (c1 < c2 ? go : 0.5f * (gc + go))) * on;
+        const float vt = h.v_target[r], eo = v - vt;
+        float c_term = eo * eo, dval = 2.f * eo * on;     // use_value_clip = False (:703-704): (values_now - v_target)^2
+        if (h.v_old) {                                    // Trick: value clip (:699-702)
+            const float vo = h.v_old[r];
+            const float dv = v - vo;
+            const float ec = fminf(fmaxf(dv, -h.eps), h.eps) + vo - vt;
+            const float c1 = ec * ec, c2 = eo * eo;
+            c_term = fmaxf(c1, c2);
+            const float gc = (dv >= -h.eps && dv <= h.eps) ? 2.f * ec : 0.f, go = 2.f * eo;
+            dval = (c1 > c2 ? gc : (c1 < c2 ? go : 0.5f * (gc + go))) * on;
+        }
         if (lane == 0) {
             h.logp[r] = lpa; h.entropy[r] = H; h.value[r] = v; h.d_value[r] = dval;
             part[0] += a_term * on; part[1] += c_term * on; part[2] += on;
@@ -668,7 +672,7 @@ extern "C" int marl_ppo_head(int64_t R, int32_t E, int32_t A, const float *d_fea
                              void *stream)
 {
     MARL_REQUIRE(R > 0 && A == MARL_NUM_ACTIONS, "marl_ppo_head: R=%lld A=%d (action_dim must be %d)", (long long)R, A, MARL_NUM_ACTIONS);
-    MARL_REQUIRE(d_feat_a && d_feat_c && d_Wa && d_ba && d_wc_eff && d_bc && d_action && d_old_logp && d_adv && d_v_old &&
+    MARL_REQUIRE(d_feat_a && d_feat_c && d_Wa && d_ba && d_wc_eff && d_bc && d_action && d_old_logp && d_adv &&
                      d_v_target && d_active && d_logp && d_entropy && d_value && d_dlogits && d_dvalue && d_sums,
                  "marl_ppo_head: null pointer");
     HeadArgs h;

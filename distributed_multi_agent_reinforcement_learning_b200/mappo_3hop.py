@@ -192,8 +192,6 @@ class MAPPO:
         self.device = torch.device(getattr(args, key))
         if self.device.type != "cuda":
             raise _lib.MarlError(f"{key}={self.device}: this engine runs on CUDA only (no CPU fallback)")
-        if not self.use_value_clip:
-            raise NotImplementedError("use_value_clip=False is not wired into the fused head kernel")
         sn = args.use_spectral_norm
         actor_gnn = GnnExtractor(self.actor_input_dim, args.gnn_middle_dim, args.gnn_output_dim, args.n_hops, sn)
         critic_gnn = GnnExtractor(self.critic_input_dim, args.gnn_middle_dim, args.gnn_output_dim, args.n_hops, sn)
@@ -251,7 +249,8 @@ class MAPPO:
                     la, lc, logp, ent, val, u2, v2 = ops.ppo_head(
                         feat_a.reshape(-1, E), feat_c.reshape(-1, E), self.actor.Mean.weight, self.actor.Mean.bias,
                         cm.weight_orig if self.sn else cm.weight, cm.bias, cm.weight_u if self.sn else torch.ones(1, device=self.device),
-                        flat(batch["a_n"][idx, :T]), flat(batch["a_logprob_n"][idx, :T]), flat(adv[idx]), flat(batch["v_n"][idx, :T]),
+                        flat(batch["a_n"][idx, :T]), flat(batch["a_logprob_n"][idx, :T]), flat(adv[idx]),
+                        flat(batch["v_n"][idx, :T]) if self.use_value_clip else None,
                         flat(v_target[idx]), flat(batch["active"][idx, :T]), self.epsilon, self.entropy_coef)
                     if self.sn:
                         with torch.no_grad():

@@ -437,8 +437,6 @@ class MAPPO:
         self.device = torch.device(getattr(a, key))
         if self.device.type != "cuda":
             raise _lib.MarlError(f"algo.{key}={self.device}: this engine runs on CUDA only (no CPU fallback)")
-        if not self.use_value_clip:
-            raise NotImplementedError("use_value_clip=False is not wired into the fused head kernel")
         if a.use_reward_norm:
             self.reward_norm = Normalization(shape=cfg.env.num_defender, device=self.device)
         encoder = DHGN(self.input_dim, self.embedding_dim, self.sn, a, self.device)
@@ -486,7 +484,7 @@ class MAPPO:
         la, lc, logp, ent, val, u2, v2 = ops.ppo_head(
             feat_a.reshape(R, E), feat_c.reshape(R, E), self.actor.Mean.weight, self.actor.Mean.bias,
             cm.weight_orig if self.sn else cm.weight, cm.bias, cm.weight_u if self.sn else torch.ones(1, device=self.device),
-            flat(mb.a), flat(mb.logp), flat(adv), flat(mb.v[:-1]), flat(v_target), flat(mb.active), self.epsilon,
+            flat(mb.a), flat(mb.logp), flat(adv), flat(mb.v[:-1]) if self.use_value_clip else None, flat(v_target), flat(mb.active), self.epsilon,
             self.entropy_coef)
         if self.sn:
             with torch.no_grad():

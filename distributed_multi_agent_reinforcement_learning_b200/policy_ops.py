@@ -462,7 +462,8 @@ class _PPOHead(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         logp, ent, val = torch.empty(R, **f32), torch.empty(R, **f32), torch.empty(R, **f32)
         dlogits, dvalue, sums = torch.empty(R, A, **f32), torch.empty(R, **f32), torch.zeros(3, **f32)
-        args = [t.contiguous() for t in (feat_a, feat_c, Wa, ba, w_eff, bc, action, old_logp, adv, v_old, v_target, active)]
+        args = [None if t is None else t.contiguous()      # v_old None: the unclipped value loss (use_value_clip = False)
+                for t in (feat_a, feat_c, Wa, ba, w_eff, bc, action, old_logp, adv, v_old, v_target, active)]
         _lib.check(_L().marl_ppo_head(R, E, A, *[_lib.ptr(t) for t in args], ctypes.c_float(eps), ctypes.c_float(ent_coef),
                                       _lib.ptr(logp), _lib.ptr(ent), _lib.ptr(val), _lib.ptr(dlogits), _lib.ptr(dvalue),
                                       _lib.ptr(sums), _lib.stream_ptr()), "marl_ppo_head")
@@ -487,7 +488,7 @@ class _PPOHead(torch.autograd.Function):
 
 
 def ppo_head(feat_a, feat_c, Wa, ba, Wc_orig, bc, u, action, old_logp, adv, v_old, v_target, active, eps, ent_coef):
-    """-> (actor_loss, critic_loss, logp [R], entropy [R], value [R], u_new, v_new)."""
+    """-> (actor_loss, critic_loss, logp [R], entropy [R], value [R], u_new, v_new).  v_old = None: no value clip."""
     return _PPOHead.apply(feat_a, feat_c, Wa, ba, Wc_orig, bc, u, action, old_logp, adv, v_old, v_target, active,
                           float(eps), float(ent_coef))
 

@@ -357,7 +357,8 @@ int marl_gru_cell_bwd(int64_t R, int32_t E, const float *d_dh_new, const float *
                       float *d_dh_prev, void *stream);
 /* Actor softmax/Categorical + critic head + PPO-clip / clipped value losses, forward AND backward in one pass
  * (:437,446-456,526,692-706).  Adds {sum actor_term*active, sum critic_term*active, sum active} to d_sums[3] and
- * writes d(sum)/d logits [R,A], d(sum)/d value [R]; the caller divides by sum(active). */
+ * writes d(sum)/d logits [R,A], d(sum)/d value [R]; the caller divides by sum(active).  d_v_old == NULL selects the unclipped
+ * value loss (values_now - v_target)^2 of use_value_clip = False (:703-704). */
 int marl_ppo_head(int64_t R, int32_t E, int32_t A, const float *d_feat_a, const float *d_feat_c, const float *d_Wa,
                   const float *d_ba, const float *d_wc_eff, const float *d_bc, const float *d_action,
                   const float *d_old_logp, const float *d_adv, const float *d_v_old, const float *d_v_target,

@@ -112,15 +112,19 @@ def train_forward(w, batch, depth, num_layers=2):
     return out["logp"], out["entropy"], out["values"]
 
 
-def ppo_losses(logp, entropy, values, batch, adv, v_target, epsilon=0.05, entropy_coef=0.05):
-    """:692-706 (value clip on)."""
+def ppo_losses(logp, entropy, values, batch, adv, v_target, epsilon=0.05, entropy_coef=0.05, use_value_clip=True):
+    """:692-706."""
     active = batch["active"]
     ratios = torch.exp(logp - batch["a_logprob_n"])
     surr1, surr2 = ratios * adv, torch.clamp(ratios, 1 - epsilon, 1 + epsilon) * adv
     actor_loss = ((-torch.min(surr1, surr2) - entropy_coef * entropy) * active).sum() / active.sum()
-    v_old = batch["v_n"][:, :-1]
-    err_clip = torch.clamp(values - v_old, -epsilon, epsilon) + v_old - v_target
-    critic_loss = (torch.max(err_clip ** 2, (values - v_target) ** 2) * active).sum() / active.sum()
+    if use_value_clip:
+        v_old = batch["v_n"][:, :-1]
+        err_clip = torch.clamp(values - v_old, -epsilon, epsilon) + v_old - v_target
+        critic_loss = torch.max(err_clip ** 2, (values - v_target) ** 2)
+    else:
+        critic_loss = (values - v_target) ** 2
+    critic_loss = (critic_loss * active).sum() / active.sum()
     return actor_loss, critic_loss
 
 

@@ -294,8 +294,8 @@ def test_gru_layer_forward_backward(E, T, R):
         torch.testing.assert_close(u.grad, v.grad, rtol=1e-4, atol=1e-5 * max(1.0, float(v.grad.abs().max())))
 
 
-@pytest.mark.parametrize("E", [128, 32])
-def test_ppo_head_forward_backward(E):
+@pytest.mark.parametrize("E,value_clip", [(128, True), (32, True), (128, False)])
+def test_ppo_head_forward_backward(E, value_clip):
     from distributed_multi_agent_reinforcement_learning_b200 import policy_ops as ops
     from oracle import policy_ref
     R, A = 301, 9
@@ -310,7 +310,7 @@ def test_ppo_head_forward_backward(E):
     adv, v_old, v_t = rn(R), rn(R) * 0.2, rn(R) * 0.2
     active = (torch.rand(R, device="cuda", generator=g) < 0.9).float()
     la = [t.clone().requires_grad_(True) for t in (feat_a, feat_c, Wa, ba, Wc, bc)]
-    out = ops.ppo_head(*la, u, action, old_logp, adv, v_old, v_t, active, 0.05, 0.05)
+    out = ops.ppo_head(*la, u, action, old_logp, adv, v_old if value_clip else None, v_t, active, 0.05, 0.05)
     (out[0] + out[1]).backward()
     # restatement: Categorical(probs=softmax) exactly as torch.distributions does it
     lb = [t.clone().requires_grad_(True) for t in (feat_a, feat_c, Wa, ba, Wc, bc)]
@@ -322,7 +322,7 @@ def test_ppo_head_forward_backward(E):
     val = torch.nn.functional.linear(lb[1], Weff, lb[5])[:, 0]
     la_ref, lc_ref = policy_ref.ppo_losses(logp[None], ent[None], val[None], {"active": active[None], "a_logprob_n": old_logp[None],
                                                                             "v_n": torch.cat([v_old[None], v_old[None, -1:]], 1)},
-                                           adv[None], v_t[None])
+                                           adv[None], v_t[None], use_value_clip=value_clip)
     torch.testing.assert_close(out[2], logp, rtol=1e-5, atol=2e-6)
     torch.testing.assert_close(out[3], ent, rtol=1e-5, atol=2e-6)
     torch.testing.assert_close(out[4], val, rtol=1e-5, atol=2e-6)
