@@ -430,6 +430,46 @@ def test_evader_hard_searches_vs_oracle(oracle):
     assert int(env.path_len[1]) > 100                         # the maze path is long
 
 
+@pytest.mark.parametrize("size", [(60, 55), (120, 60), (200, 62)])
+def test_evader_cup_trap_search_vs_oracle(oracle, size):
+    """The evader starts inside a cup that opens away from its target: the weighted A* floods the cup before it finds the way
+    round (1.5 K pops and ~160 OPEN entries on the default map, 4.5 K pops and ~420 entries on 200 x 62 - stripes of the OPEN
+    list many entries long, dead-end pops, every column loop with more columns than lanes).  Path, length and the evader's move
+    must equal the oracle's."""
+    from distributed_multi_agent_reinforcement_learning_b200 import default_config, maps
+    from distributed_multi_agent_reinforcement_learning_b200.pursuit_env import BatchedPursuitEnv
+    W, H = size
+    cfg = default_config(env__num_defender=4, map__map_size=[W, H])
+    grid = np.zeros((W, H), np.uint8)
+    x0 = W // 2
+    grid[x0, 4:H - 4] = 1
+    grid[x0 - W // 4:x0 + 1, 4] = 1
+    grid[x0 - W // 4:x0 + 1, H - 5] = 1                        # (< 176 boundary cells: the obstacle slots of the sensor tables)
+    grids = grid[None]
+    env = BatchedPursuitEnv(cfg, 1, num_maps=1)
+    env.set_maps(grids)
+    p_state = np.zeros((1, 4, 4))
+    p_state[0, :, 0] = [1, 2, 3, 4]                            # pursuers parked in a corner
+    p_state[0, :, 1] = 1.0
+    e_state = np.array([[x0 - 5.2, H // 2 + 0.1, 0, 0]], np.float64)
+    target = np.array([[W - 4, H // 2]], np.int32)
+    env.set_state(p_state, e_state, target, np.arange(1), time_step=0)
+    env.start_episode()
+    env.set_target_tape(np.zeros((1, 0, 2), np.int32))
+    env.evader_step()
+    torch.cuda.synchronize()
+    assert not (env.evader_status.cpu().numpy() & 3).any()
+    p = oracle.EnvParams.from_dict(env.params.as_dict())
+    infl = maps.dilate(grids, 2)
+    ev = oracle.EvaderState(e_state[0], target[0])
+    assert oracle.evader_step(p, ev, p_state[0], 0, grids[0], infl[0], np.zeros((0, 2), np.int32)) in (0, -2)
+    L = ev.path_len.value
+    assert L > W // 4                                          # out of the cup and round the wall
+    assert int(env.path_len[0]) == L
+    assert np.array_equal(env.path[0, :L].cpu().numpy(), ev.path[:L])
+    np.testing.assert_allclose(env.e_state[0].cpu().numpy(), ev.e_state, rtol=1e-9, atol=1e-9)
+
+
 def test_grouped_multistream_rollout_is_identical():
     """Sub-batches on separate streams (and inside a CUDA graph) give bit-identical arenas and final states."""
     from distributed_multi_agent_reinforcement_learning_b200 import default_config
