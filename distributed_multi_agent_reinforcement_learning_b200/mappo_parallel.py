@@ -19,6 +19,7 @@ Reference quirks kept on purpose (parity is defined per phase):
   * minibatches are sequential, unshuffled index ranges (:665).
 """
 import os
+import time
 
 import numpy as np
 import torch
@@ -518,6 +519,7 @@ class MAPPO:
         if allreduce not in (None, "update", "minibatch"):
             raise ValueError(f"allreduce={allreduce!r}: None / 'update' (one all-reduce per update) or 'minibatch'")
         per_mb = allreduce == "minibatch"
+        t_issue = time.perf_counter()
         if shuffle is None:
             shuffle = bool(getattr(self.cfg.algo, "shuffle_minibatches", False)) or permutation is not None
         data = replay_buffer.get_training_data(self.device) if hasattr(replay_buffer, "get_training_data") else replay_buffer
@@ -590,6 +592,7 @@ class MAPPO:
                     ops.clip_grad_norm_(flat, 5.0)
         self.ac_optimizer._sync_grads()
         self._grads_reduced = per_mb
+        self.last_train_issue_s = time.perf_counter() - t_issue     # host time to ISSUE the epoch (the device may still be running)
         lh = losses.cpu()
         if trace is not None:
             for m, rec in enumerate(trace["mb"]):
