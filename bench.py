@@ -82,9 +82,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t0 = [], None, index, None
 
     def start(self):
+        """Launched BEFORE the warm-up (nvidia-smi needs a few hundred ms to print its first row); `mark()` opens the timed region."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -93,21 +94,29 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        self.t0 = time.monotonic()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.15)                                   # the row that covers the end of the timed region
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        t0 = self.t0 if self.t0 is not None else 0.0
+        rows = [r for t, r in self.rows if t >= t0]        # rows printed inside the timed region (+ the one right after it)
+        scope = "timed region"
+        if not any(r and r[0].isdigit() for r in rows):    # a very short region: fall back to the warm-up + timed region
+            rows, scope = [r for _, r in self.rows], "warm-up + timed region"
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "sampled_over": scope}
 
 
 def policy_flops_per_agent(N, O, D, head=2304):
@@ -438,11 +447,12 @@ def run_ours(args):
 
     # ---- value: whole episode with the networks in the loop, HBM-resident -----------------------------------
     restore = lambda: env.restore(snap)
-    timed(pol.replay, args.warmup, restore)
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
+    timed(pol.replay, args.warmup, restore)
+    barrier()
+    sampler.mark()
     ms_total = timed(pol.replay, args.steps, restore)
     barrier()
     clocks = sampler.stop() if rank == 0 else None

@@ -913,7 +913,10 @@ class MAPPO:
                 host_out["episode_reward"].copy_(arena.raw_reward[:T].sum(dim=(0, 2), dtype=torch.int64), non_blocking=True)
             if "collision" in host_out:
                 host_out["collision"].copy_(engine.collision, non_blocking=True)
+            status = engine.evader_status.max()
             torch.cuda.current_stream().synchronize()
+            if int(status):                                  # the evader's search overflowed or its target tape ran out: not an episode
+                raise _lib.MarlError(f"explore_batched: evader status {int(status)} (A* OPEN / path overflow or target tape exhausted)")
         return g.batch
 
     def _train_batch(self, engine, arena, T, oxy, hist_a, hist_c, v, logp):
