@@ -22,7 +22,7 @@ def main():
     dev = torch.device("cuda", 0)
     cfg = bench.make_cfg()
     B, M, T = bench.B_PER_GPU, bench.N_MAPS, bench.T_STEPS
-    wl = bench.host_workload(cfg, B, M, seed=0xB200 + 1)
+    wl = bench.host_workload(cfg, B, M, seed=0xB200 + 1 + 7919 * int(os.environ.get("EVADER_RANK", "0")))      # bench.py's per-rank workload
     env = BatchedPursuitEnv(cfg, B, device=dev, num_maps=M)
     env.set_maps(wl["grids"], wl["inflated"])
     env.set_state(wl["p_state"], wl["e_state"], wl["target"], wl["map_id"], time_step=0)
