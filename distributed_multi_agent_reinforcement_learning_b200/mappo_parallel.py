@@ -800,7 +800,10 @@ class MAPPO:
         dev = self.device
         main = torch.cuda.current_stream()
         if len(getattr(engine, "_pipe_streams", [])) < 2 * G:
-            engine._pipe_streams = [torch.cuda.Stream(device=dev) for _ in range(2 * G)]
+            # MARL_PIPE_PRIORITY (measurement knob): "astar" / "policy" gives the A* side streams / the policy streams the high priority
+            prio = os.environ.get("MARL_PIPE_PRIORITY", "")
+            engine._pipe_streams = [torch.cuda.Stream(device=dev, priority=(-1 if (prio == "astar" and i % 2 == 1) or (prio == "policy" and i % 2 == 0) else 0))
+                                    for i in range(2 * G)]
         rec_ptrs = arena.record_pointers()
         diff = int(engine.params.difficulty)
         full_tile = (128 // N) * N if N <= 128 else 0      # concurrent launches: full tiles, SMs left over for the neighbours

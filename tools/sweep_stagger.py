@@ -25,9 +25,12 @@ def main():
     snap = env.snapshot()
     torch.manual_seed(0xB200)
     mappo = MAPPO(cfg, B, max(1, round(B / 10)), "Learner")
-    combos = [tuple(int(v) for v in c.split(":")) for c in (sys.argv[1:] or ["4:0", "4:2", "4:3", "4:5", "6:2", "8:2"])]
-    for pipes, stag in combos:
-        os.environ["MARL_PIPELINES"], os.environ["MARL_STAGGER"] = str(pipes), str(stag)
+    # pipelines:stagger[:priority]  (priority = astar | policy: which streams get the high CUDA stream priority)
+    combos = [c.split(":") for c in (sys.argv[1:] or ["4:0", "4:2", "4:3", "4:5", "6:2", "8:2"])]
+    for combo in combos:
+        pipes, stag, prio = int(combo[0]), int(combo[1]), (combo[2] if len(combo) > 2 else "")
+        os.environ["MARL_PIPELINES"], os.environ["MARL_STAGGER"], os.environ["MARL_PIPE_PRIORITY"] = str(pipes), str(stag), prio
+        env._pipe_streams = []
         env.restore(snap)
         g = RolloutGraph(mappo, env, arena, T, 0xB200)
         ts = []
@@ -39,7 +42,7 @@ def main():
             b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        print(f"pipelines {pipes} stagger {stag}: {min(ts[1:]):.2f} ms per episode (median {sorted(ts[1:])[2]:.2f})", flush=True)
+        print(f"pipelines {pipes} stagger {stag} priority {prio or '-'}: {min(ts[1:]):.2f} ms per episode (median {sorted(ts[1:])[2]:.2f})", flush=True)
         del g
 
 
